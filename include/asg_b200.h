@@ -1,0 +1,164 @@
+/*
+ * asg_b200.h -- C ABI of libasg_b200.so: the ASG-loss hot path of zh217/torch-asg rebuilt as
+ * hand-written sm_100a CUDA.  Plain pointers and sizes only; no torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (/root/reference/torch_asg/native):
+ *
+ *   asg_scan()   the four alpha/beta recursions and everything they drag along:
+ *                  fully_connected_alpha_recursion   fully_connected_lattice.cpp:9-29
+ *                  fully_connected_beta_recursion    fully_connected_lattice.cpp:32-47
+ *                  make_aligned_inputs_{cpu,gpu}     force_aligned_lattice.cpp:15-46, _kernel.cu:9-105
+ *                  make_aligned_transition_{cpu,gpu} force_aligned_lattice.cpp:48-82, _kernel.cu:136-226
+ *                  force_aligned_alpha_recursion     force_aligned_lattice.cpp:84-111
+ *                  force_aligned_beta_recursion      force_aligned_lattice.cpp:113-154
+ *                  roll_to_end / should_roll_to_end  utils.cpp:22-66   (replaced by in-kernel length predicates)
+ *                  the score read-outs               fully_connected_lattice.cpp:89, force_aligned_lattice.cpp:316
+ *                and the stream choreography of fast_asg_gpu_forward{,_only}
+ *                  (streamlined_fast_gpu.cpp:24-94, :104-230): the "roles" mask selects which of the four
+ *                  scans run; each (utterance, scan) pair is its own CTA and the FCC and FAC launches overlap on two streams.
+ *   asg_grad()   the no-recursion gradient assembly:
+ *                  fully_connected_derivative/backward  fully_connected_lattice.cpp:50-63, :94-104
+ *                  force_aligned_derivative/backward    force_aligned_lattice.cpp:156-183, :321-356
+ *                  collect_input_grad_{cpu,gpu}         force_aligned_lattice.cpp:234-264, _kernel.cu:370-470
+ *                  collect_transition_grad_{cpu,gpu}    force_aligned_lattice.cpp:204-231, _kernel.cu:255-344
+ *                  fast_asg_gpu_backward                streamlined_fast_gpu.cpp:236-297
+ *   asg_host_*() the whole ASGLoss forward+backward (asg.py:109-142) for callers that hold HOST buffers
+ *                (the end-to-end path bench.py times; H2D/D2H copies are inside the call).
+ *
+ * Conventions (BASELINE.json letters): emissions x[T,N,L] (batch is dim 1), transition A[L,L] with
+ * A[i,j] = score of going from j to i, targets y[N,S] int64, lengths il[N], tl[N] int64.
+ * All strides are in ELEMENTS.  Every function returns 0 on success, a negative ASG_E_* code on a bad
+ * argument, or a positive cudaError_t; asg_last_error() describes the last failure of the calling thread.
+ * All work is enqueued on `stream`; nothing synchronises the host unless stated.
+ *
+ * Intermediate state is NOT the reference's log-domain alpha/beta: see DESIGN.md "Numerics".  The FCC
+ * states are real-domain vectors rescaled by one power of two per frame; the FAC states are block
+ * floating point (one power-of-two exponent per 8 target positions per frame).
+ */
+#ifndef ASG_B200_H
+#define ASG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *asg_stream_t; /* a cudaStream_t */
+
+enum { ASG_F32 = 0, ASG_F64 = 1 };
+
+/* asg_scan(): which recursions to run */
+enum {
+    ASG_ROLE_FCC_ALPHA = 1,
+    ASG_ROLE_FCC_BETA = 2,
+    ASG_ROLE_FAC_ALPHA = 4,
+    ASG_ROLE_FAC_BETA = 8,
+    ASG_ROLE_ALL = 15,
+    ASG_ROLE_FORWARD_ONLY = 10 /* the two beta scans: fast_asg_gpu_forward_only */
+};
+
+/* asg_grad(): which lattice's gradients to assemble */
+enum { ASG_PART_FCC = 1, ASG_PART_FAC = 2, ASG_PART_BOTH = 3 };
+
+enum {
+    ASG_OK = 0,
+    ASG_E_DTYPE = -1,   /* dtype is not ASG_F32 / ASG_F64 */
+    ASG_E_SHAPE = -2,   /* non-positive T/N/L/S, or S > T (asg.py:119-122 truncates before the boundary) */
+    ASG_E_NULL = -3,    /* a required pointer is NULL */
+    ASG_E_UNSUPPORTED = -4, /* shape outside what this build covers (see asg_layout) */
+    ASG_E_NOGPU = -5    /* no CUDA device / driver: there is no CPU fallback */
+};
+
+/* Sizes and offsets of the opaque buffers a caller allocates for one (dtype,T,N,L,S) problem. */
+typedef struct asg_layout {
+    int64_t sp;               /* row pitch (elements) of the FAC state arrays: S rounded up to 8 */
+    int64_t nblk;             /* block exponents per (frame, utterance): sp / 8 */
+    size_t elem_bytes;        /* 4 or 8 */
+    size_t fcc_state_bytes;   /* one FCC state array  [T,N,L]   */
+    size_t fac_state_bytes;   /* one FAC state array  [T,N,sp]  */
+    size_t ctx_bytes;         /* the context blob handed from asg_scan() to asg_grad() */
+    size_t grad_scratch_bytes;/* scratch for asg_grad() (per-CTA partial sums) */
+    /* byte offsets inside the context blob (all 256-byte aligned) */
+    size_t off_ehat;          /* [L,L]     exp(A - R)                         */
+    size_t off_fcc_scale;     /* [T,N]     power-of-two applied to alpha at frame t */
+    size_t off_fcc_w;         /* [T,N,L]   u_t * beta_t (emission-weighted beta)    */
+    size_t off_fac_hd;        /* [2,N,sp]  exp(H - Rb), exp(D - Rb)           */
+    size_t off_fac_ea;        /* [T,N,nblk] int32 block exponents of FAC alpha */
+    size_t off_fac_eb;        /* [T,N,nblk] int32 block exponents of FAC beta  */
+    size_t off_lengths;       /* [2,N] int64 copies of il, tl                 */
+    size_t off_scalars;       /* [N,8] float64: per-utterance log-scale bookkeeping (scores in f64 etc.) */
+} asg_layout_t;
+
+/* Fills *out.  Returns ASG_E_UNSUPPORTED for shapes this build does not cover. */
+int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout_t *out);
+
+/*
+ * Forward recursions.  Outputs whose role is not selected may be NULL.  fcc_beta / fac_beta may also be
+ * NULL when their role IS selected: the beta scans then only produce the scores (forward-only mode,
+ * nothing is stored -- fast_asg_gpu_forward_only, streamlined_fast_gpu.cpp:24-94).
+ *   fcc_alpha, fcc_beta : [T,N,L]   device, dtype
+ *   fac_alpha, fac_beta : [T,N,sp]  device, dtype
+ *   ctx                 : ctx_bytes device (always required)
+ *   full_scores         : [N] dtype, written when ASG_ROLE_FCC_BETA is selected
+ *   aligned_scores      : [N] dtype, written when ASG_ROLE_FAC_BETA is selected
+ * il/tl are DEVICE pointers (NULL = full lengths T / S).
+ */
+int asg_scan(int dtype, int roles,
+             const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl,
+             const void *A, int64_t A_s0, int64_t A_s1,
+             const int64_t *y, int64_t y_s0, int64_t y_s1,
+             const int64_t *il, const int64_t *tl,
+             int64_t T, int64_t N, int64_t L, int64_t S,
+             void *fcc_alpha, void *fcc_beta, void *fac_alpha, void *fac_beta, void *ctx,
+             void *full_scores, void *aligned_scores,
+             asg_stream_t stream);
+
+/*
+ * Gradient assembly.  grad_x [T,N,L] (contiguous) and grad_A [L,L] are fully overwritten:
+ *   grad_x = softmax-posterior(FCC) * g_full  +  scatter(softmax-posterior(FAC) * g_aligned)
+ *   grad_A = likewise for the transition matrix
+ * i.e. the two upstream vectors are applied independently and the FAC part is ADDED, exactly like
+ * fast_asg_gpu_backward (streamlined_fast_gpu.cpp:261-287); autograd supplies g_aligned = -g_full.
+ * g_full/g_aligned: [N] dtype device, element strides g*_stride (0 = broadcast scalar).
+ * `parts` selects FCC only / FAC only / both; unused inputs may be NULL.
+ */
+int asg_grad(int dtype, int parts,
+             const void *g_full, int64_t g_full_stride,
+             const void *g_aligned, int64_t g_aligned_stride,
+             const void *fcc_alpha, const void *fcc_beta,
+             const void *fac_alpha, const void *fac_beta, const void *ctx,
+             const int64_t *y, int64_t y_s0, int64_t y_s1,
+             int64_t T, int64_t N, int64_t L, int64_t S,
+             void *grad_x, void *grad_A, void *scratch,
+             asg_stream_t stream);
+
+/* ---- host-buffer convenience API (end-to-end path) ------------------------------------------- */
+typedef struct asg_host_ctx asg_host_ctx_t;
+
+/* Allocates device + pinned staging buffers for problems up to (T,N,L,S) on `device`. */
+int asg_host_create(int dtype, int device, int64_t T, int64_t N, int64_t L, int64_t S, asg_host_ctx_t **out);
+void asg_host_destroy(asg_host_ctx_t *h);
+
+/*
+ * One ASGLoss forward+backward from HOST memory: copies x, A, y, il, tl to the device, runs the four
+ * scans and the gradient assembly, copies loss[N] (= full - aligned), grad_x[T,N,L] and grad_A[L,L]
+ * back, and waits for completion.  g[N] is the upstream gradient on the per-utterance loss
+ * (NULL = all ones, i.e. reduction 'sum').  grad_x / grad_A may be NULL (forward only: the two beta
+ * scans alone run, like ASGLoss(forward_only=True)).  x, y contiguous.
+ */
+int asg_host_loss(asg_host_ctx_t *h,
+                  const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
+                  const void *g, int64_t T, int64_t N, int64_t L, int64_t S,
+                  void *loss, void *grad_x, void *grad_A);
+
+const char *asg_last_error(void);
+const char *asg_version(void);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t asg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASG_B200_H */

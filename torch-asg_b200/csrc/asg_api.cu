@@ -1,0 +1,278 @@
+// asg_api.cu -- the extern "C" surface of libasg_b200.so (see include/asg_b200.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "asg_common.cuh"
+#include "asg_internal.h"
+
+namespace asg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(int e, const char *where) {
+    if (e == 0) return 0;
+    return fail(e, "%s: CUDA error %d (%s)", where, e, cudaGetErrorString((cudaError_t)e));
+}
+
+static int check_dims(int dtype, int64_t T, int64_t N, int64_t L, int64_t S) {
+    if (dtype != ASG_F32 && dtype != ASG_F64) return fail(ASG_E_DTYPE, "dtype must be ASG_F32 or ASG_F64, got %d", dtype);
+    if (T <= 0 || N <= 0 || L <= 0 || S <= 0)
+        return fail(ASG_E_SHAPE, "T, N, L, S must be positive (got %lld, %lld, %lld, %lld)", (long long)T, (long long)N,
+                    (long long)L, (long long)S);
+    if (S > T) return fail(ASG_E_SHAPE, "S (%lld) > T (%lld): truncate targets first (asg.py:119-122)", (long long)S, (long long)T);
+    if (L > 64) return fail(ASG_E_UNSUPPORTED, "this build covers L <= 64 labels (got %lld)", (long long)L);
+    if (S > 4096) return fail(ASG_E_UNSUPPORTED, "this build covers S <= 4096 target positions (got %lld)", (long long)S);
+    if (T > (1 << 24) || N > (1 << 20)) return fail(ASG_E_UNSUPPORTED, "T or N too large");
+    return 0;
+}
+
+}  // namespace asg
+
+using namespace asg;
+
+template <typename T>
+static int scan_typed(int roles, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0,
+                      int64_t A_s1, const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl,
+                      const asg_layout_t &lay, int64_t Tt, int64_t N, int64_t L, int64_t S, void *fcc_alpha, void *fcc_beta,
+                      void *fac_alpha, void *fac_beta, void *ctx, void *full_scores, void *aligned_scores,
+                      cudaStream_t stream) {
+    ScanArgs<T> a;
+    a.x = (const T *)x; a.x_st = x_st; a.x_sn = x_sn; a.x_sl = x_sl;
+    a.A = (const T *)A; a.A_s0 = A_s0; a.A_s1 = A_s1;
+    a.y = y; a.y_s0 = y_s0; a.y_s1 = y_s1;
+    a.il = il; a.tl = tl;
+    a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
+    a.fcc_alpha = (T *)fcc_alpha; a.fcc_beta = (T *)fcc_beta;
+    a.fac_alpha = (T *)fac_alpha; a.fac_beta = (T *)fac_beta;
+    a.ctx = make_ctx<T>(ctx, lay, N);
+    a.full_scores = (T *)full_scores; a.aligned_scores = (T *)aligned_scores;
+    a.role0 = a.role1 = 0;
+    return launch_scan<T>(a, roles, stream);
+}
+
+template <typename T>
+static int grad_typed(int parts, const void *g_full, int64_t gfs, const void *g_al, int64_t gas, const void *fcc_alpha,
+                      const void *fcc_beta, const void *fac_alpha, const void *fac_beta, const void *ctx, const int64_t *y,
+                      int64_t y_s0, int64_t y_s1, const asg_layout_t &lay, int64_t Tt, int64_t N, int64_t L, int64_t S,
+                      void *grad_x, void *grad_A, void *scratch, cudaStream_t stream) {
+    GradArgs<T> a;
+    a.g_full = (const T *)g_full; a.g_full_stride = gfs;
+    a.g_aligned = (const T *)g_al; a.g_aligned_stride = gas;
+    a.fcc_alpha = (const T *)fcc_alpha; a.fcc_beta = (const T *)fcc_beta;
+    a.fac_alpha = (const T *)fac_alpha; a.fac_beta = (const T *)fac_beta;
+    a.ctx = make_ctx<T>(const_cast<void *>(ctx), lay, N);
+    a.y = y; a.y_s0 = y_s0; a.y_s1 = y_s1;
+    a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
+    a.grad_x = (T *)grad_x; a.grad_A = (T *)grad_A;
+    a.partials = (T *)scratch;
+    a.tb = 0; a.tiles_t = 0; a.num_tiles = 0;
+    return launch_grad<T>(a, parts, stream);
+}
+
+struct asg_host_ctx {
+    int dtype, device;
+    int64_t T, N, L, S;
+    asg_layout_t lay;
+    cudaStream_t stream;
+    char *dev;          // one device slab
+    size_t dev_bytes;
+    // offsets into the slab
+    size_t o_x, o_A, o_y, o_il, o_tl, o_g, o_gneg, o_fa, o_fb, o_aa, o_ab, o_ctx, o_full, o_al, o_loss, o_gx, o_gA, o_scr;
+};
+
+template <typename T> __global__ void host_loss_kernel(const T *full, const T *aligned, T *loss, int N) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) loss[n] = full[n] - aligned[n];
+}
+template <typename T> __global__ void host_g_kernel(const T *g, T *gpos, T *gneg, int N, int have_g) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) { T v = have_g ? g[n] : T(1); gpos[n] = v; gneg[n] = -v; }
+}
+
+extern "C" {
+
+int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout_t *out) {
+    if (!out) return fail(ASG_E_NULL, "asg_layout: out is NULL");
+    int rc = check_dims(dtype, T, N, L, S);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    const size_t eb = dtype == ASG_F32 ? 4 : 8;
+    out->elem_bytes = eb;
+    out->sp = (S + ASG_BLK - 1) / ASG_BLK * ASG_BLK;
+    out->nblk = out->sp / ASG_BLK;
+    out->fcc_state_bytes = eb * (size_t)T * N * L;
+    out->fac_state_bytes = eb * (size_t)T * N * out->sp;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    out->off_ehat = take(eb * (size_t)L * L);
+    out->off_fcc_scale = take(eb * (size_t)T * N);
+    out->off_fcc_w = take(eb * (size_t)T * N * L);
+    out->off_fac_hd = take(eb * 2 * (size_t)N * out->sp);
+    out->off_fac_ea = take(sizeof(int) * (size_t)T * N * out->nblk);
+    out->off_fac_eb = take(sizeof(int) * (size_t)T * N * out->nblk);
+    out->off_lengths = take(sizeof(int64_t) * 2 * (size_t)N);
+    out->off_scalars = take(sizeof(double) * 8 * (size_t)N);
+    out->ctx_bytes = off;
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) device = -1;
+    out->grad_scratch_bytes = align_up(eb * (size_t)grad_grid_size(device) * L * L, 256);
+    return 0;
+}
+
+int asg_scan(int dtype, int roles, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0,
+             int64_t A_s1, const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl, int64_t T,
+             int64_t N, int64_t L, int64_t S, void *fcc_alpha, void *fcc_beta, void *fac_alpha, void *fac_beta, void *ctx,
+             void *full_scores, void *aligned_scores, asg_stream_t stream) {
+    asg_layout_t lay;
+    int rc = asg_layout(dtype, T, N, L, S, &lay);
+    if (rc) return rc;
+    if ((roles & ~ASG_ROLE_ALL) || roles == 0) return fail(ASG_E_SHAPE, "asg_scan: bad roles mask %d", roles);
+    if (!x || !A || !ctx) return fail(ASG_E_NULL, "asg_scan: x, A and ctx are required");
+    if ((roles & ASG_ROLE_FCC_ALPHA) && !fcc_alpha) return fail(ASG_E_NULL, "asg_scan: fcc_alpha is NULL");
+    if ((roles & ASG_ROLE_FAC_ALPHA) && !fac_alpha) return fail(ASG_E_NULL, "asg_scan: fac_alpha is NULL");
+    if ((roles & (ASG_ROLE_FAC_ALPHA | ASG_ROLE_FAC_BETA)) && !y) return fail(ASG_E_NULL, "asg_scan: y is NULL");
+    int e;
+    if (dtype == ASG_F32)
+        e = scan_typed<float>(roles, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, lay, T, N, L, S, fcc_alpha,
+                              fcc_beta, fac_alpha, fac_beta, ctx, full_scores, aligned_scores, (cudaStream_t)stream);
+    else
+        e = scan_typed<double>(roles, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, lay, T, N, L, S, fcc_alpha,
+                               fcc_beta, fac_alpha, fac_beta, ctx, full_scores, aligned_scores, (cudaStream_t)stream);
+    return cuda_fail(e, "asg_scan");
+}
+
+int asg_grad(int dtype, int parts, const void *g_full, int64_t g_full_stride, const void *g_aligned,
+             int64_t g_aligned_stride, const void *fcc_alpha, const void *fcc_beta, const void *fac_alpha,
+             const void *fac_beta, const void *ctx, const int64_t *y, int64_t y_s0, int64_t y_s1, int64_t T, int64_t N,
+             int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch, asg_stream_t stream) {
+    asg_layout_t lay;
+    int rc = asg_layout(dtype, T, N, L, S, &lay);
+    if (rc) return rc;
+    if (parts < 1 || parts > 3) return fail(ASG_E_SHAPE, "asg_grad: bad parts mask %d", parts);
+    if (!ctx || !grad_x || !grad_A || !scratch) return fail(ASG_E_NULL, "asg_grad: ctx, grad_x, grad_A, scratch are required");
+    if ((parts & ASG_PART_FCC) && (!g_full || !fcc_alpha || !fcc_beta)) return fail(ASG_E_NULL, "asg_grad: FCC inputs missing");
+    if ((parts & ASG_PART_FAC) && (!g_aligned || !fac_alpha || !fac_beta || !y))
+        return fail(ASG_E_NULL, "asg_grad: FAC inputs missing");
+    int e;
+    if (dtype == ASG_F32)
+        e = grad_typed<float>(parts, g_full, g_full_stride, g_aligned, g_aligned_stride, fcc_alpha, fcc_beta, fac_alpha,
+                              fac_beta, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch, (cudaStream_t)stream);
+    else
+        e = grad_typed<double>(parts, g_full, g_full_stride, g_aligned, g_aligned_stride, fcc_alpha, fcc_beta, fac_alpha,
+                               fac_beta, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch, (cudaStream_t)stream);
+    return cuda_fail(e, "asg_grad");
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer API
+// ---------------------------------------------------------------------------------------------
+int asg_host_create(int dtype, int device, int64_t T, int64_t N, int64_t L, int64_t S, asg_host_ctx_t **out) {
+    if (!out) return fail(ASG_E_NULL, "asg_host_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        return fail(ASG_E_NOGPU, "asg_host_create: CUDA device %d is not available (no CPU fallback exists)", device);
+    int e = cudaSetDevice(device);
+    if (e) return cuda_fail(e, "cudaSetDevice");
+    asg_host_ctx *h = new (std::nothrow) asg_host_ctx();
+    if (!h) return fail(ASG_E_NULL, "out of host memory");
+    h->dtype = dtype; h->device = device; h->T = T; h->N = N; h->L = L; h->S = S;
+    int rc = asg_layout(dtype, T, N, L, S, &h->lay);
+    if (rc) { delete h; return rc; }
+    const size_t eb = h->lay.elem_bytes;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    h->o_x = take(eb * (size_t)T * N * L);
+    h->o_A = take(eb * (size_t)L * L);
+    h->o_y = take(8 * (size_t)N * S);
+    h->o_il = take(8 * (size_t)N);
+    h->o_tl = take(8 * (size_t)N);
+    h->o_g = take(eb * (size_t)N);
+    h->o_gneg = take(eb * (size_t)N);
+    h->o_fa = take(h->lay.fcc_state_bytes);
+    h->o_fb = take(h->lay.fcc_state_bytes);
+    h->o_aa = take(h->lay.fac_state_bytes);
+    h->o_ab = take(h->lay.fac_state_bytes);
+    h->o_ctx = take(h->lay.ctx_bytes);
+    h->o_full = take(eb * (size_t)N);
+    h->o_al = take(eb * (size_t)N);
+    h->o_loss = take(eb * (size_t)N);
+    h->o_gx = take(eb * (size_t)T * N * L);
+    h->o_gA = take(eb * (size_t)L * L);
+    h->o_scr = take(h->lay.grad_scratch_bytes);
+    h->dev_bytes = off;
+    if ((e = cudaMalloc((void **)&h->dev, off))) { delete h; return cuda_fail(e, "cudaMalloc"); }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking))) { cudaFree(h->dev); delete h; return cuda_fail(e, "cudaStreamCreate"); }
+    *out = h;
+    return 0;
+}
+
+void asg_host_destroy(asg_host_ctx_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamDestroy(h->stream);
+    cudaFree(h->dev);
+    delete h;
+}
+
+int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
+                  const void *g, int64_t T, int64_t N, int64_t L, int64_t S, void *loss, void *grad_x, void *grad_A) {
+    if (!h || !x || !A || !y || !loss) return fail(ASG_E_NULL, "asg_host_loss: h, x, A, y, loss are required");
+    if (T != h->T || N != h->N || L != h->L || S != h->S)
+        return fail(ASG_E_SHAPE, "asg_host_loss: shape differs from the one the context was created for");
+    int e = cudaSetDevice(h->device);
+    if (e) return cuda_fail(e, "cudaSetDevice");
+    const size_t eb = h->lay.elem_bytes;
+    cudaStream_t st = h->stream;
+    char *d = h->dev;
+    const bool want_grad = grad_x != nullptr || grad_A != nullptr;
+#define ASG_TRY(call, what) do { if ((e = (int)(call))) return cuda_fail(e, what); } while (0)
+    ASG_TRY(cudaMemcpyAsync(d + h->o_x, x, eb * (size_t)T * N * L, cudaMemcpyHostToDevice, st), "H2D x");
+    ASG_TRY(cudaMemcpyAsync(d + h->o_A, A, eb * (size_t)L * L, cudaMemcpyHostToDevice, st), "H2D A");
+    ASG_TRY(cudaMemcpyAsync(d + h->o_y, y, 8 * (size_t)N * S, cudaMemcpyHostToDevice, st), "H2D y");
+    if (il) ASG_TRY(cudaMemcpyAsync(d + h->o_il, il, 8 * (size_t)N, cudaMemcpyHostToDevice, st), "H2D il");
+    if (tl) ASG_TRY(cudaMemcpyAsync(d + h->o_tl, tl, 8 * (size_t)N, cudaMemcpyHostToDevice, st), "H2D tl");
+    if (g && want_grad) ASG_TRY(cudaMemcpyAsync(d + h->o_g, g, eb * (size_t)N, cudaMemcpyHostToDevice, st), "H2D g");
+    const int roles = want_grad ? ASG_ROLE_ALL : ASG_ROLE_FORWARD_ONLY;
+    int rc = asg_scan(h->dtype, roles, d + h->o_x, N * L, L, 1, d + h->o_A, L, 1, (const int64_t *)(d + h->o_y), S, 1,
+                      il ? (const int64_t *)(d + h->o_il) : nullptr, tl ? (const int64_t *)(d + h->o_tl) : nullptr, T, N, L, S,
+                      d + h->o_fa, d + h->o_fb, d + h->o_aa, d + h->o_ab, d + h->o_ctx, d + h->o_full, d + h->o_al, st);
+    if (rc) return rc;
+    const int nb = (int)((N + 127) / 128);
+    if (h->dtype == ASG_F32) host_loss_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_full), (float *)(d + h->o_al), (float *)(d + h->o_loss), (int)N);
+    else host_loss_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_full), (double *)(d + h->o_al), (double *)(d + h->o_loss), (int)N);
+    count_launch();
+    ASG_TRY(cudaMemcpyAsync(loss, d + h->o_loss, eb * (size_t)N, cudaMemcpyDeviceToHost, st), "D2H loss");
+    if (want_grad) {
+        if (h->dtype == ASG_F32) host_g_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_g), (float *)(d + h->o_g), (float *)(d + h->o_gneg), (int)N, g != nullptr);
+        else host_g_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_g), (double *)(d + h->o_g), (double *)(d + h->o_gneg), (int)N, g != nullptr);
+        count_launch();
+        rc = asg_grad(h->dtype, ASG_PART_BOTH, d + h->o_g, 1, d + h->o_gneg, 1, d + h->o_fa, d + h->o_fb, d + h->o_aa,
+                      d + h->o_ab, d + h->o_ctx, (const int64_t *)(d + h->o_y), S, 1, T, N, L, S, d + h->o_gx, d + h->o_gA,
+                      d + h->o_scr, st);
+        if (rc) return rc;
+        if (grad_x) ASG_TRY(cudaMemcpyAsync(grad_x, d + h->o_gx, eb * (size_t)T * N * L, cudaMemcpyDeviceToHost, st), "D2H grad_x");
+        if (grad_A) ASG_TRY(cudaMemcpyAsync(grad_A, d + h->o_gA, eb * (size_t)L * L, cudaMemcpyDeviceToHost, st), "D2H grad_A");
+    }
+    ASG_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+#undef ASG_TRY
+    return 0;
+}
+
+const char *asg_last_error(void) { return g_err; }
+const char *asg_version(void) { return "asg_b200 0.1 (sm_100a)"; }
+uint64_t asg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// asg_common.cuh -- device helpers shared by the scan and gradient-assembly kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define ASG_FULL_MASK 0xffffffffu
+#define ASG_BLK 8                 // FAC states per lane = per block-floating-point exponent
+
+namespace asg {
+
+// ---------------------------------------------------------------------------------------------
+// scalar traits
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Num;
+
+template <> struct Num<float> {
+    static constexpr int kMaxShift = 126;
+    __device__ __forceinline__ static float exp_(float v) { return expf(v); }
+    __device__ __forceinline__ static float log_(float v) { return logf(v); }
+    __device__ __forceinline__ static float neg_inf() { return __int_as_float(0xff800000); }
+    // 2^k for k in [-126,127] (clamped)
+    __device__ __forceinline__ static float exp2i(int k) {
+        k = max(-126, min(127, k));
+        return __int_as_float((k + 127) << 23);
+    }
+    // For M >= 0: power-of-two `scale` with M*scale in [1,2) and e = -log2(scale).  M == 0, inf or
+    // NaN leave the value alone.  A denormal M is only pulled up by 2^126 (the next frame finishes).
+    __device__ __forceinline__ static void pow2_norm(float M, float &scale, int &e) {
+        int biased = (__float_as_int(M) >> 23) & 0xff;
+        bool live = (M > 0.0f) && (biased != 0xff);
+        biased = max(1, min(253, biased));
+        e = live ? biased - 127 : 0;
+        scale = live ? __int_as_float((254 - biased) << 23) : 1.0f;
+    }
+    // max over the warp of a NON-NEGATIVE value: IEEE order == unsigned integer order -> one REDUX
+    __device__ __forceinline__ static float warp_max_nonneg(float v) {
+        return __uint_as_float(__reduce_max_sync(ASG_FULL_MASK, __float_as_uint(v)));
+    }
+    // max over the warp of any (non-NaN) value via an order-preserving signed key
+    __device__ __forceinline__ static float warp_max(float v) {
+        int b = __float_as_int(v);
+        int key = b ^ ((b >> 31) & 0x7fffffff);
+        key = __reduce_max_sync(ASG_FULL_MASK, key);
+        return __int_as_float(key ^ ((key >> 31) & 0x7fffffff));
+    }
+};
+
+template <> struct Num<double> {
+    static constexpr int kMaxShift = 1022;
+    __device__ __forceinline__ static double exp_(double v) { return exp(v); }
+    __device__ __forceinline__ static double log_(double v) { return log(v); }
+    __device__ __forceinline__ static double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+    __device__ __forceinline__ static double exp2i(int k) {
+        k = max(-1022, min(1023, k));
+        return __hiloint2double((k + 1023) << 20, 0);
+    }
+    __device__ __forceinline__ static void pow2_norm(double M, double &scale, int &e) {
+        int biased = (__double2hiint(M) >> 20) & 0x7ff;
+        bool live = (M > 0.0) && (biased != 0x7ff);
+        biased = max(1, min(2045, biased));
+        e = live ? biased - 1023 : 0;
+        scale = live ? __hiloint2double((2046 - biased) << 20, 0) : 1.0;
+    }
+    __device__ __forceinline__ static double warp_max_nonneg(double v) { return warp_max(v); }
+    __device__ __forceinline__ static double warp_max(double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(ASG_FULL_MASK, v, o));
+        return v;
+    }
+};
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ASG_FULL_MASK, v, o);
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+
+// ---------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) -- element-granular so arbitrary (element-aligned) strides are accepted
+// ---------------------------------------------------------------------------------------------
+template <int BYTES> __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// volatile shared-memory progress counters (producer/consumer rings)
+__device__ __forceinline__ int ld_volatile_s32(const int *p) {
+    int v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_s32(int *p, int v) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.s32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory");
+}
+
+// named barrier over `nthreads` threads (ids 1.. ; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// streaming (evict-first) global stores for state arrays that are written once and read once later
+template <typename T> __device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace asg

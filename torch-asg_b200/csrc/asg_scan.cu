@@ -1,0 +1,679 @@
+// asg_scan.cu -- the four ASG recursions as persistent, warp-specialised sm_100a scan kernels.
+//
+// Replaces (reference, /root/reference/torch_asg/native):
+//   fully_connected_alpha_recursion / _beta_recursion   fully_connected_lattice.cpp:9-29, :32-47
+//   force_aligned_alpha_recursion / _beta_recursion     force_aligned_lattice.cpp:84-111, :113-154
+//   make_aligned_inputs / make_aligned_transition       force_aligned_lattice.cpp:15-82 (+ _kernel.cu)
+//   roll_to_end                                         utils.cpp:40-66 (length predicates instead)
+//   score read-outs                                     fully_connected_lattice.cpp:89, force_aligned_lattice.cpp:316
+//
+// Shape of the computation: the T axis is strictly serial, so every (utterance, recursion) pair is
+// one latency-bound chain.  Each chain gets its own CTA: one (FCC) or W (FAC) *consumer* warps that do
+// nothing but the recurrence, fed by one *producer* warp that streams the utterance's emission rows
+// from HBM with a cp.async ring, turns them into per-frame-normalised exponentials u_t = exp(x_t - max x_t)
+// (and, for FAC, gathers them into target order) and publishes them through a shared-memory ring.
+// The recurrences run in the real domain -- no exp/log on the critical path:
+//   FCC: P_t = s_t * u_t o (E P_{t-1}),  E = exp(A - max A) held in REGISTERS (one row per lane, the
+//        rows beyond 32 split four-ways by column), s_t = exact power of two from a single REDUX max.
+//   FAC: bidiagonal; 8 consecutive target positions per lane, block floating point (one power-of-two
+//        exponent per lane), neighbours exchanged with one shuffle; no warp-wide reduction at all.
+// See DESIGN.md for the numerics and tests/scaled_model.py for the executable specification.
+#include "asg_common.cuh"
+#include "asg_internal.h"
+
+namespace asg {
+
+// =============================================================================================
+// FCC
+// =============================================================================================
+constexpr int FCC_PF = 16;   // cp.async rows in flight
+constexpr int FCC_D = 16;    // depth of the u ring
+
+template <typename T, int LP>
+struct FccSmem {
+    T raw[FCC_PF][LP];
+    T uring[FCC_D][LP];
+    T mxring[FCC_D];
+    alignas(16) T pvec[2][LP];
+    int produced;
+    int consumed;
+};
+
+template <typename T>
+__device__ __forceinline__ T ehat_of(const T *A, int64_t s0, int64_t s1, int i, int j, int L, T R) {
+    if (i >= L || j >= L) return T(0);
+    T a = A[i * s0 + j * s1];
+    return (a == Num<T>::neg_inf()) ? T(0) : Num<T>::exp_(a - R);
+}
+
+// max over the finite entries of A (0 if there are none), computed by one warp
+template <typename T>
+__device__ __forceinline__ T transition_max(const T *A, int64_t s0, int64_t s1, int L, int lane) {
+    T m = Num<T>::neg_inf();
+    for (int e = lane; e < L * L; e += 32) {
+        T a = A[(e / L) * s0 + (e % L) * s1];
+        if (a < -Num<T>::neg_inf()) m = tmax(m, a);   // skips +inf and NaN
+    }
+    m = Num<T>::warp_max(m);
+    return (m > Num<T>::neg_inf()) ? m : T(0);
+}
+
+template <typename T, int LP, bool BETA>
+__device__ void fcc_producer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) {
+    const int L = a.d.L;
+    const T *xn = a.x + (int64_t)n * a.x_sn;
+    auto issue = [&](int k) {
+        const int t = BETA ? (Tn - 1 - k) : k;
+        const T *row = xn + (int64_t)t * a.x_st;
+        if (lane < L) cp_async<sizeof(T)>(&sm.raw[k % FCC_PF][lane], row + (int64_t)lane * a.x_sl);
+        if (LP > 32 && lane + 32 < L) cp_async<sizeof(T)>(&sm.raw[k % FCC_PF][lane + 32], row + (int64_t)(lane + 32) * a.x_sl);
+    };
+    for (int k = 0; k < FCC_PF; ++k) {
+        if (k < Tn) issue(k);
+        cp_async_commit();
+    }
+    for (int k = 0; k < Tn; ++k) {
+        cp_async_wait<FCC_PF - 1>();
+        const T ninf = Num<T>::neg_inf();
+        T v0 = (lane < L) ? sm.raw[k % FCC_PF][lane] : ninf;
+        T v1 = (LP > 32 && lane + 32 < L) ? sm.raw[k % FCC_PF][lane + 32] : ninf;
+        if (k + FCC_PF < Tn) issue(k + FCC_PF);
+        cp_async_commit();
+        T m = Num<T>::warp_max(tmax(v0, v1));
+        if (!(m > ninf)) m = T(0);                     // an all -inf frame
+        T u0 = (lane < L) ? Num<T>::exp_(v0 - m) : T(0);
+        T u1 = (LP > 32 && lane + 32 < L) ? Num<T>::exp_(v1 - m) : T(0);
+        if (k >= FCC_D) {
+            while (ld_volatile_s32(&sm.consumed) < k - FCC_D + 1) __nanosleep(40);
+        }
+        const int slot = k % FCC_D;
+        if (lane < LP) sm.uring[slot][lane] = u0;
+        if (LP > 32 && lane + 32 < LP) sm.uring[slot][lane + 32] = u1;
+        if (lane == 0) sm.mxring[slot] = m;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            st_volatile_s32(&sm.produced, k + 1);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <typename T, int LP, bool BETA>
+__device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) {
+    constexpr bool FULL = (LP >= 32);
+    constexpr int REM = FULL ? LP - 32 : LP;                      // rows handled with a column split
+    constexpr int RP = REM <= 8 ? 8 : (REM <= 16 ? 16 : 32);
+    constexpr int CH = 32 / RP;                                   // column chunks
+    constexpr int CL = LP / CH;                                   // columns per chunk
+    constexpr int RBASE = FULL ? 32 : 0;
+    const int L = a.d.L, N = a.d.N;
+    const int rr = lane % RP, cc = lane / RP;
+    const int row2 = RBASE + rr;
+    const bool has2 = (REM > 0) && (rr < REM);
+
+    // ---- transition matrix -> registers (real domain, max-normalised) -------------------------
+    const T R = transition_max(a.A, a.A_s0, a.A_s1, L, lane);
+    T E1[FULL ? LP : 1];
+    T E2[REM > 0 ? CL : 1];
+    if (FULL) {
+#pragma unroll
+        for (int j = 0; j < LP; ++j)
+            E1[j] = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, j, L, R);
+    }
+    if (REM > 0) {
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+            const int j = cc * CL + c;
+            E2[c] = !has2 ? T(0)
+                          : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j, L, R));
+        }
+    }
+    if (!BETA && n == 0) {   // publish E for the gradient assembly
+        for (int e = lane; e < L * L; e += 32) a.ctx.ehat[e] = ehat_of(a.A, a.A_s0, a.A_s1, e / L, e % L, L, R);
+    }
+    if (!BETA && lane == 0) a.ctx.il[n] = Tn;
+
+    T *state = BETA ? a.fcc_beta : a.fcc_alpha;
+    int ready = 0;
+    int esum = 0;
+    double msum = 0.0;
+    int cur = 0;
+    T v1 = T(0), v2 = T(0);     // this lane's rows of the current state vector
+    T last_w1 = T(0), last_w2 = T(0);
+
+    for (int k = 0; k < Tn; ++k) {
+        const int t = BETA ? (Tn - 1 - k) : k;
+        if (k >= ready) {
+            while ((ready = ld_volatile_s32(&sm.produced)) <= k) __nanosleep(20);
+            __threadfence_block();
+        }
+        const int slot = k % FCC_D;
+        const T u1 = FULL ? sm.uring[slot][lane] : T(0);
+        const T u2 = has2 ? sm.uring[slot][row2] : T(0);
+        msum += (double)sm.mxring[slot];
+        T sc = T(1);
+        if (k == 0) {
+            if (BETA) { v1 = (FULL && lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
+            else { v1 = u1; v2 = u2; }
+        } else {
+            // ---- z = E p (alpha) / E^T w (beta) ------------------------------------------------
+            const T *pv = sm.pvec[cur];
+            T z2 = T(0);
+            if (REM > 0) {
+                T acc0 = T(0), acc1 = T(0);
+#pragma unroll
+                for (int c = 0; c < CL; c += 2) {
+                    acc0 = fma(E2[c], pv[cc * CL + c], acc0);
+                    if (c + 1 < CL) acc1 = fma(E2[c + 1], pv[cc * CL + c + 1], acc1);
+                }
+                z2 = acc0 + acc1;
+#pragma unroll
+                for (int o = RP; o < 32; o <<= 1) z2 += __shfl_xor_sync(ASG_FULL_MASK, z2, o);
+            }
+            T z1 = T(0);
+            if (FULL) {
+                T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+                for (int j = 0; j < LP; ++j) acc[j & 3] = fma(E1[j], pv[j], acc[j & 3]);
+                z1 = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            }
+            if (BETA) { v1 = z1; v2 = z2; }
+            else { v1 = z1 * u1; v2 = z2 * u2; }
+            const T M = Num<T>::warp_max_nonneg(tmax(v1, v2));
+            int e;
+            Num<T>::pow2_norm(M, sc, e);
+            v1 *= sc; v2 *= sc;
+            esum += e;
+        }
+        // ---- publish the new state ---------------------------------------------------------------
+        const int64_t base = ((int64_t)t * N + n) * L;
+        T w1 = v1, w2 = v2;                       // what feeds the next mat-vec
+        if (BETA) { w1 = v1 * u1; w2 = v2 * u2; }
+        if (FULL) {
+            sm.pvec[cur ^ 1][lane] = w1;
+            if (lane < L && state) {
+                st_stream(state + base + lane, v1);
+                if (BETA) st_stream(a.ctx.fcc_w + base + lane, w1);
+            }
+        }
+        if (has2 && cc == 0) {
+            sm.pvec[cur ^ 1][row2] = w2;
+            if (row2 < L && state) {
+                st_stream(state + base + row2, v2);
+                if (BETA) st_stream(a.ctx.fcc_w + base + row2, w2);
+            }
+        }
+        if (!FULL && !has2 && cc == 0 && row2 < LP) sm.pvec[cur ^ 1][row2] = T(0);
+        if (!BETA && lane == 0) a.ctx.fcc_scale[(int64_t)t * N + n] = sc;
+        last_w1 = w1; last_w2 = w2;
+        cur ^= 1;
+        __syncwarp();
+        if (lane == 0) st_volatile_s32(&sm.consumed, k + 1);
+    }
+    // ---- score: log(sum of the final weighted state) + bookkeeping -----------------------------
+    if (Tn > 0) {
+        T tot = warp_sum((FULL ? last_w1 : T(0)) + ((has2 && cc == 0) ? last_w2 : T(0)));
+        if (lane == 0) {
+            const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
+                                 (double)esum * 0.6931471805599453094;
+            a.ctx.scalars[(int64_t)n * 8 + (BETA ? SC_FULL_BETA : SC_FULL_ALPHA)] = score;
+            a.ctx.scalars[(int64_t)n * 8 + SC_R] = (double)R;
+            if (BETA && a.full_scores) a.full_scores[n] = (T)score;
+        }
+    } else if (lane == 0 && BETA && a.full_scores) {
+        a.full_scores[n] = T(0);
+    }
+}
+
+template <typename T, int LP>
+__global__ void __launch_bounds__(64) fcc_scan_kernel(const ScanArgs<T> a) {
+    __shared__ FccSmem<T, LP> sm;
+    const int n = blockIdx.x;
+    const int role = blockIdx.y == 0 ? a.role0 : a.role1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { sm.produced = 0; sm.consumed = 0; }
+    __syncthreads();
+    int Tn = a.il ? (int)a.il[n] : a.d.T;
+    Tn = max(0, min(Tn, a.d.T));
+    if (role == 0) {
+        if (warp == 0) fcc_consumer<T, LP, false>(a, sm, n, Tn, lane);
+        else fcc_producer<T, LP, false>(a, sm, n, Tn, lane);
+    } else {
+        if (warp == 0) fcc_consumer<T, LP, true>(a, sm, n, Tn, lane);
+        else fcc_producer<T, LP, true>(a, sm, n, Tn, lane);
+    }
+}
+
+// =============================================================================================
+// FAC
+// =============================================================================================
+constexpr int FAC_PF = 8;    // cp.async rows in flight
+
+template <typename T> struct FacSmemView {
+    T *raw;        // [FAC_PF][L]
+    T *urow;       // [L]
+    T *gring;      // [D][sp]
+    T *mxring;     // [D]
+    T *xval;       // [2][W+1]  boundary mantissas between consumer warps
+    int *xexp;     // [2][W+1]
+    int *ylab;     // [sp]
+    T *red;        // [W]
+    int *produced; // [1]
+    int *consumed; // [W]
+};
+
+template <typename T>
+__host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, int L, int sp, int W, int D) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
+    size_t o_raw = take(sizeof(T) * FAC_PF * L);
+    size_t o_urow = take(sizeof(T) * L);
+    size_t o_gring = take(sizeof(T) * (size_t)D * sp);
+    size_t o_mx = take(sizeof(T) * D);
+    size_t o_xval = take(sizeof(T) * 2 * (W + 1));
+    size_t o_xexp = take(sizeof(int) * 2 * (W + 1));
+    size_t o_ylab = take(sizeof(int) * sp);
+    size_t o_red = take(sizeof(T) * W);
+    size_t o_prod = take(sizeof(int) * 4);
+    size_t o_cons = take(sizeof(int) * W);
+    if (v) {
+        v->raw = (T *)(base + o_raw); v->urow = (T *)(base + o_urow); v->gring = (T *)(base + o_gring);
+        v->mxring = (T *)(base + o_mx); v->xval = (T *)(base + o_xval); v->xexp = (int *)(base + o_xexp);
+        v->ylab = (int *)(base + o_ylab); v->red = (T *)(base + o_red); v->produced = (int *)(base + o_prod);
+        v->consumed = (int *)(base + o_cons);
+    }
+    return off;
+}
+
+template <typename T, int W, bool BETA>
+__device__ void fac_producer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, int Tn, int Sn, int D, int lane) {
+    const int L = a.d.L;
+    const int sp = (int)a.ctx.sp;
+    const T *xn = a.x + (int64_t)n * a.x_sn;
+    auto issue = [&](int k) {
+        const int t = BETA ? (Tn - 1 - k) : k;
+        const T *row = xn + (int64_t)t * a.x_st;
+        T *dst = sm.raw + (size_t)(k % FAC_PF) * L;
+        for (int i = lane; i < L; i += 32) cp_async<sizeof(T)>(dst + i, row + (int64_t)i * a.x_sl);
+    };
+    for (int k = 0; k < FAC_PF; ++k) {
+        if (k < Tn) issue(k);
+        cp_async_commit();
+    }
+    const T ninf = Num<T>::neg_inf();
+    for (int k = 0; k < Tn; ++k) {
+        cp_async_wait<FAC_PF - 1>();
+        const T *src = sm.raw + (size_t)(k % FAC_PF) * L;
+        T m = ninf;
+        for (int i = lane; i < L; i += 32) m = tmax(m, src[i]);
+        m = Num<T>::warp_max(m);
+        if (!(m > ninf)) m = T(0);
+        for (int i = lane; i < L; i += 32) sm.urow[i] = Num<T>::exp_(src[i] - m);
+        if (k + FAC_PF < Tn) issue(k + FAC_PF);   // this lane's own elements of the slot are consumed
+        cp_async_commit();
+        __syncwarp();
+        if (k >= D) {
+            const int need = k - D + 1;
+            for (;;) {
+                int c = (lane < W) ? ld_volatile_s32(&sm.consumed[lane]) : 0x7fffffff;
+                c = __reduce_min_sync(ASG_FULL_MASK, c);
+                if (c >= need) break;
+                __nanosleep(40);
+            }
+        }
+        T *g = sm.gring + (size_t)(k % D) * sp;
+        for (int s = lane; s < sp; s += 32) {
+            const int lab = sm.ylab[s];
+            g[s] = (lab >= 0) ? sm.urow[lab] : T(0);
+        }
+        if (lane == 0) sm.mxring[k % D] = m;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            st_volatile_s32(sm.produced, k + 1);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <typename T, int W>
+__device__ __forceinline__ void fac_consumer_sync() {
+    if (W == 1) __syncwarp();
+    else named_bar_sync(1, 32 * W);
+}
+
+template <typename T, int W, bool BETA>
+__device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, int Tn, int Sn, int D, T Rb,
+                             const T (&h)[ASG_BLK], const T (&dd)[ASG_BLK], int warp, int lane) {
+    // dd[j]: alpha -> edge (s-1 -> s) into own state j;  beta -> edge (s -> s+1) out of own state j
+    const int N = a.d.N;
+    const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk;
+    const int gl = warp * 32 + lane;            // global lane = block index
+    const int s0 = gl * ASG_BLK;
+    const bool owns = s0 < sp;
+    T *state = BETA ? a.fac_beta : a.fac_alpha;
+    int *estate = BETA ? a.ctx.fac_eb : a.ctx.fac_ea;
+
+    T v[ASG_BLK];        // alpha: P ; beta: Q (mantissas)
+    T w[ASG_BLK];        // beta only: emission-weighted state fed to the next step
+    int Eme = 0;
+    T mymax = T(0);      // max of what feeds the next step (alpha: v, beta: w)
+    int ready = 0;
+    double msum = 0.0;
+    int cur = 0;
+
+    for (int k = 0; k < Tn; ++k) {
+        const int t = BETA ? (Tn - 1 - k) : k;
+        if (k >= ready) {
+            while ((ready = ld_volatile_s32(sm.produced)) <= k) __nanosleep(20);
+            __threadfence_block();
+        }
+        const T *g = sm.gring + (size_t)(k % D) * sp;
+        T ub[ASG_BLK];
+#pragma unroll
+        for (int j = 0; j < ASG_BLK; ++j) ub[j] = owns ? g[s0 + j] : T(0);
+        msum += (double)sm.mxring[k % D];
+
+        if (k == 0) {
+#pragma unroll
+            for (int j = 0; j < ASG_BLK; ++j) {
+                if (BETA) v[j] = (s0 + j == Sn - 1) ? T(1) : T(0);
+                else v[j] = (s0 + j == 0) ? ub[j] : T(0);
+            }
+        } else {
+            // neighbour's boundary value and exponent from the previous step
+            T nv; int ne;
+            const T src = BETA ? w[0] : v[ASG_BLK - 1];
+            if (BETA) { nv = __shfl_down_sync(ASG_FULL_MASK, src, 1); ne = __shfl_down_sync(ASG_FULL_MASK, Eme, 1); }
+            else { nv = __shfl_up_sync(ASG_FULL_MASK, src, 1); ne = __shfl_up_sync(ASG_FULL_MASK, Eme, 1); }
+            if (!BETA && lane == 0) {
+                if (W > 1 && warp > 0) { nv = sm.xval[cur * (W + 1) + warp - 1]; ne = sm.xexp[cur * (W + 1) + warp - 1]; }
+                else { nv = T(0); ne = Eme; }
+            }
+            if (BETA && lane == 31) {
+                if (W > 1 && warp < W - 1) { nv = sm.xval[cur * (W + 1) + warp + 1]; ne = sm.xexp[cur * (W + 1) + warp + 1]; }
+                else { nv = T(0); ne = Eme; }
+            }
+            if (mymax == T(0)) Eme = ne;                       // an empty block adopts its neighbour's exponent
+            nv *= Num<T>::exp2i(ne - Eme);
+            T r[ASG_BLK];
+            if (BETA) {
+#pragma unroll
+                for (int j = 0; j < ASG_BLK; ++j) {
+                    const T nxt = (j + 1 < ASG_BLK) ? w[(j + 1) % ASG_BLK] : nv;
+                    r[j] = fma(h[j], w[j], dd[j] * nxt);
+                }
+                if (s0 + ASG_BLK - 1 > t) {                    // band: position s is reachable by frame t only if s <= t
+#pragma unroll
+                    for (int j = 0; j < ASG_BLK; ++j) if (s0 + j > t) r[j] = T(0);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < ASG_BLK; ++j) {
+                    const T prv = (j > 0) ? v[(j + ASG_BLK - 1) % ASG_BLK] : nv;
+                    r[j] = ub[j] * fma(h[j], v[j], dd[j] * prv);
+                }
+                const int lb = (Sn - 1) - (Tn - 1 - t);        // band: positions below lb can no longer finish
+                if (s0 < lb) {
+#pragma unroll
+                    for (int j = 0; j < ASG_BLK; ++j) if (s0 + j < lb) r[j] = T(0);
+                }
+            }
+            T m = r[0];
+#pragma unroll
+            for (int j = 1; j < ASG_BLK; ++j) m = tmax(m, r[j]);
+            T sc; int e;
+            Num<T>::pow2_norm(m, sc, e);
+#pragma unroll
+            for (int j = 0; j < ASG_BLK; ++j) v[j] = r[j] * sc;
+            Eme += e;
+        }
+        // what feeds the next step, and its max
+        if (BETA) {
+#pragma unroll
+            for (int j = 0; j < ASG_BLK; ++j) w[j] = v[j] * ub[j];
+        }
+        mymax = BETA ? w[0] : v[0];
+#pragma unroll
+        for (int j = 1; j < ASG_BLK; ++j) mymax = tmax(mymax, BETA ? w[j] : v[j]);
+
+        // store mantissas + exponent
+        if (owns && state) {
+            T *dst = state + ((int64_t)t * N + n) * sp + s0;
+#pragma unroll
+            for (int j = 0; j < ASG_BLK; ++j) st_stream(dst + j, v[j]);
+            if (gl < nblk) estate[((int64_t)t * N + n) * nblk + gl] = Eme;
+        }
+        if (W > 1) {
+            if (!BETA && lane == 31) { sm.xval[(cur ^ 1) * (W + 1) + warp] = v[ASG_BLK - 1]; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
+            if (BETA && lane == 0) { sm.xval[(cur ^ 1) * (W + 1) + warp] = w[0]; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
+        }
+        cur ^= 1;
+        fac_consumer_sync<T, W>();
+        if (lane == 0) st_volatile_s32(&sm.consumed[warp], k + 1);
+    }
+    // ---- score ------------------------------------------------------------------------------------
+    if (gl == 0) {
+        double score = 0.0;
+        if (Tn > 0) {
+            // beta: w[0] = u_0[y_0] * Q_0[0];  alpha: total mass in the final position S_n-1 is read below
+            const T fin = BETA ? w[0] : T(0);
+            score = (double)Num<T>::log_(fin) + msum + (double)(Tn - 1) * (double)Rb + (double)Eme * 0.6931471805599453094;
+        }
+        if (BETA) {
+            a.ctx.scalars[(int64_t)n * 8 + SC_AL_BETA] = score;
+            a.ctx.scalars[(int64_t)n * 8 + SC_RB] = (double)Rb;
+            if (a.aligned_scores) a.aligned_scores[n] = (T)score;
+        }
+    }
+    if (!BETA && Tn > 0) {      // alpha-side score (cross-check): mass at (T_n-1, S_n-1)
+        const int sl = Sn - 1;
+        if (sl >= s0 && sl < s0 + ASG_BLK) {
+            T fin = T(0);
+#pragma unroll
+            for (int j = 0; j < ASG_BLK; ++j) if (s0 + j == sl) fin = v[j];
+            a.ctx.scalars[(int64_t)n * 8 + SC_AL_ALPHA] =
+                (double)Num<T>::log_(fin) + msum + (double)(Tn - 1) * (double)Rb + (double)Eme * 0.6931471805599453094;
+        }
+    }
+}
+
+template <typename T, int W>
+__global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T> a, int D) {
+    extern __shared__ __align__(16) char smem_raw[];
+    FacSmemView<T> sm;
+    const int L = a.d.L, S = a.d.S;
+    const int sp = (int)a.ctx.sp;
+    fac_smem_carve<T>(&sm, smem_raw, L, sp, W, D);
+    const int n = blockIdx.x;
+    const int role = blockIdx.y == 0 ? a.role0 : a.role1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nthreads = 32 * W + 32;
+
+    int Tn = a.il ? (int)a.il[n] : a.d.T;
+    Tn = max(0, min(Tn, a.d.T));
+    int Sn = a.tl ? (int)a.tl[n] : S;
+    Sn = max(1, min(Sn, S));
+
+    if (threadIdx.x == 0) sm.produced[0] = 0;
+    if (threadIdx.x < W) sm.consumed[threadIdx.x] = 0;
+    const int64_t *yn = a.y + (int64_t)n * a.y_s0;
+    for (int s = threadIdx.x; s < sp; s += nthreads) {
+        int lab = -1;
+        if (s < Sn) { lab = (int)yn[(int64_t)s * a.y_s1]; lab = max(0, min(L - 1, lab)); }
+        sm.ylab[s] = lab;
+    }
+    __syncthreads();
+
+    // ---- per-position transition scores: H_s = A[y_s,y_s], D_s = A[y_{s+1},y_s]; Rb = their max ----
+    const bool consumer = warp < W;
+    const int gl = warp * 32 + lane;
+    const int s0 = gl * ASG_BLK;
+    const T ninf = Num<T>::neg_inf();
+    T Hs[ASG_BLK], Ds[ASG_BLK];   // log-domain; Ds: edge s -> s+1
+    T lmax = ninf;
+    if (consumer) {
+#pragma unroll
+        for (int j = 0; j < ASG_BLK; ++j) {
+            const int s = s0 + j;
+            Hs[j] = ninf; Ds[j] = ninf;
+            if (s < Sn) {
+                const int c = sm.ylab[s];
+                Hs[j] = a.A[c * a.A_s0 + c * a.A_s1];
+                if (s + 1 < Sn) { const int nx = sm.ylab[s + 1]; Ds[j] = a.A[nx * a.A_s0 + c * a.A_s1]; }
+                if (Hs[j] < -ninf) lmax = tmax(lmax, Hs[j]);
+                if (Ds[j] < -ninf) lmax = tmax(lmax, Ds[j]);
+            }
+        }
+        lmax = Num<T>::warp_max(lmax);
+        if (lane == 0) sm.red[warp] = lmax;
+    }
+    __syncthreads();
+    T Rb = ninf;
+    for (int q = 0; q < W; ++q) Rb = tmax(Rb, sm.red[q]);
+    if (!(Rb > ninf)) Rb = T(0);
+
+    if (!consumer) {
+        if (role == 0) fac_producer<T, W, false>(a, sm, n, Tn, Sn, D, lane);
+        else fac_producer<T, W, true>(a, sm, n, Tn, Sn, D, lane);
+        return;
+    }
+    T h[ASG_BLK], dout[ASG_BLK];
+#pragma unroll
+    for (int j = 0; j < ASG_BLK; ++j) {
+        h[j] = (Hs[j] == ninf) ? T(0) : Num<T>::exp_(Hs[j] - Rb);
+        dout[j] = (Ds[j] == ninf) ? T(0) : Num<T>::exp_(Ds[j] - Rb);
+    }
+    if (role == 0) {
+        // publish h, d for the gradient assembly, and the lengths
+        if (s0 < sp) {
+#pragma unroll
+            for (int j = 0; j < ASG_BLK; ++j) {
+                a.ctx.fac_hd[(int64_t)n * sp + s0 + j] = h[j];
+                a.ctx.fac_hd[((int64_t)a.d.N + n) * sp + s0 + j] = dout[j];
+            }
+        }
+        if (gl == 0) { a.ctx.il[n] = Tn; a.ctx.tl[n] = Sn; }
+        // alpha needs the edge INTO each own position: d_{s-1}
+        T din[ASG_BLK];
+        T left = __shfl_up_sync(ASG_FULL_MASK, dout[ASG_BLK - 1], 1);
+        if (lane == 0) {
+            // previous warp's last lane: recompute from A directly
+            left = T(0);
+            if (s0 > 0 && s0 < Sn) {
+                const int c = sm.ylab[s0 - 1], nx = sm.ylab[s0];
+                const T dv = a.A[nx * a.A_s0 + c * a.A_s1];
+                left = (dv == ninf) ? T(0) : Num<T>::exp_(dv - Rb);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ASG_BLK; ++j) din[j] = (j == 0) ? left : dout[(j + ASG_BLK - 1) % ASG_BLK];
+        fac_consumer<T, W, false>(a, sm, n, Tn, Sn, D, Rb, h, din, warp, lane);
+    } else {
+        fac_consumer<T, W, true>(a, sm, n, Tn, Sn, D, Rb, h, dout, warp, lane);
+    }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static cudaStream_t side_stream(int device) {
+    static cudaStream_t streams[64] = {0};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!streams[device]) cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+    return streams[device];
+}
+static cudaEvent_t pooled_event(int device, int which) {
+    static cudaEvent_t ev[64][2] = {{0}};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!ev[device][which]) cudaEventCreateWithFlags(&ev[device][which], cudaEventDisableTiming);
+    return ev[device][which];
+}
+
+template <typename T, int LP>
+static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
+    dim3 grid(a.d.N, nroles);
+    fcc_scan_kernel<T, LP><<<grid, 64, 0, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T> static cudaError_t launch_fcc(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
+    const int L = a.d.L;
+    if (L <= 8) return launch_fcc_lp<T, 8>(a, nroles, st);
+    if (L <= 16) return launch_fcc_lp<T, 16>(a, nroles, st);
+    if (L <= 24) return launch_fcc_lp<T, 24>(a, nroles, st);
+    if (L <= 32) return launch_fcc_lp<T, 32>(a, nroles, st);
+    if (L <= 40) return launch_fcc_lp<T, 40>(a, nroles, st);
+    if (L <= 48) return launch_fcc_lp<T, 48>(a, nroles, st);
+    if (L <= 56) return launch_fcc_lp<T, 56>(a, nroles, st);
+    if (L <= 64) return launch_fcc_lp<T, 64>(a, nroles, st);
+    return cudaErrorInvalidValue;
+}
+
+template <typename T, int W>
+static cudaError_t launch_fac_w(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
+    const int L = a.d.L, sp = (int)a.ctx.sp;
+    int D = 16;
+    size_t bytes = fac_smem_carve<T>(nullptr, nullptr, L, sp, W, D);
+    while (bytes > 200 * 1024 && D > 2) { D >>= 1; bytes = fac_smem_carve<T>(nullptr, nullptr, L, sp, W, D); }
+    if (bytes > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(fac_scan_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid(a.d.N, nroles);
+    fac_scan_kernel<T, W><<<grid, 32 * W + 32, bytes, st>>>(a, D);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T> static cudaError_t launch_fac(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
+    const int lanes = (int)a.ctx.nblk;
+    if (lanes <= 32) return launch_fac_w<T, 1>(a, nroles, st);
+    if (lanes <= 64) return launch_fac_w<T, 2>(a, nroles, st);
+    if (lanes <= 128) return launch_fac_w<T, 4>(a, nroles, st);
+    if (lanes <= 256) return launch_fac_w<T, 8>(a, nroles, st);
+    if (lanes <= 512) return launch_fac_w<T, 16>(a, nroles, st);
+    return cudaErrorInvalidValue;
+}
+
+template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaStream_t stream) {
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return (int)e;
+    const bool fcc_a = roles & ASG_ROLE_FCC_ALPHA, fcc_b = roles & ASG_ROLE_FCC_BETA;
+    const bool fac_a = roles & ASG_ROLE_FAC_ALPHA, fac_b = roles & ASG_ROLE_FAC_BETA;
+    const bool any_fcc = fcc_a || fcc_b, any_fac = fac_a || fac_b;
+    cudaStream_t side = nullptr;
+    if (any_fcc && any_fac) {
+        // the FAC scans run beside the FCC scans: fork a side stream off the caller's stream, join after
+        side = side_stream(device);
+        cudaEvent_t fork = pooled_event(device, 0);
+        if ((e = cudaEventRecord(fork, stream)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return (int)e;
+    }
+    if (any_fcc) {
+        ScanArgs<T> a = a_in;
+        a.role0 = fcc_a ? 0 : 1;
+        a.role1 = 1;
+        if ((e = launch_fcc<T>(a, (fcc_a && fcc_b) ? 2 : 1, stream)) != cudaSuccess) return (int)e;
+    }
+    if (any_fac) {
+        ScanArgs<T> a = a_in;
+        a.role0 = fac_a ? 0 : 1;
+        a.role1 = 1;
+        cudaStream_t st = side ? side : stream;
+        if ((e = launch_fac<T>(a, (fac_a && fac_b) ? 2 : 1, st)) != cudaSuccess) return (int)e;
+        if (side) {
+            cudaEvent_t join = pooled_event(device, 1);
+            if ((e = cudaEventRecord(join, side)) != cudaSuccess) return (int)e;
+            if ((e = cudaStreamWaitEvent(stream, join, 0)) != cudaSuccess) return (int)e;
+        }
+    }
+    return 0;
+}
+
+template int launch_scan<float>(const ScanArgs<float> &, int, cudaStream_t);
+template int launch_scan<double>(const ScanArgs<double> &, int, cudaStream_t);
+
+}  // namespace asg

@@ -1,0 +1,254 @@
+// torch_binding.cpp -- the Python module `torch_asg_native`: the seven functions the reference registers
+// in native/extension.cpp:15-29, same names, same positional arguments, same tuple returns, implemented as
+// thin calls into the C ABI of libasg_b200.so (include/asg_b200.h).  torch is plumbing here: it owns the
+// device memory and the current stream, nothing else.
+//
+// What the returned "alpha / beta / gamma / path_contrib" tensors hold differs from the reference by design
+// (asg.py only looks at alpha.shape / full_gamma.shape -- asg.py:28,50,88 -- and hands everything else
+// straight back to our own backward):
+//   alpha / full_gamma         scaled real-domain FCC alpha  [T,N,L]
+//   aligned alpha / gamma      block-floating-point FAC alpha, a [T,N,S] view of a [T,N,sp] buffer
+//   beta                       the matching beta state
+//   path_contrib               an opaque uint8 context blob (asg_layout_t) -- NOT a [T-1,N,L,L] tensor
+// There is no CPU path: CPU tensors raise.
+#include <torch/extension.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include "../../include/asg_b200.h"
+
+namespace {
+
+using at::Tensor;
+
+int dtype_code(const Tensor &t, const char *what) {
+    if (t.scalar_type() == at::kFloat) return ASG_F32;
+    if (t.scalar_type() == at::kDouble) return ASG_F64;
+    TORCH_CHECK(false, "expected scalar type Float or Double but found ", t.scalar_type(), " for ", what);
+    return -1;
+}
+
+void check_cuda(const Tensor &t, const char *what) {
+    TORCH_CHECK(t.is_cuda(), "torch_asg_native (B200 build): '", what,
+                "' must be a CUDA tensor -- this extension has no CPU implementation and no fallback");
+}
+
+// lengths / targets: int64 only, like the reference (utils.cpp:28,46; force_aligned_lattice.cpp:31-33)
+Tensor as_device_long(const Tensor &t, const Tensor &like, const char *what) {
+    TORCH_CHECK(t.scalar_type() == at::kLong, "expected scalar type Long but found ", t.scalar_type(), " for ", what);
+    Tensor r = t;
+    if (r.device() != like.device()) r = r.to(like.device(), /*non_blocking=*/true);
+    return r.contiguous();
+}
+
+void check_rc(int rc) { TORCH_CHECK(rc == 0, "asg_b200: ", asg_last_error(), " (code ", rc, ")"); }
+
+asg_layout_t layout_of(int dtype, int64_t T, int64_t N, int64_t L, int64_t S) {
+    asg_layout_t lay;
+    check_rc(asg_layout(dtype, T, N, L, S, &lay));
+    return lay;
+}
+
+Tensor bytes_like(const Tensor &like, size_t nbytes) {
+    return at::empty({(int64_t)nbytes}, like.options().dtype(at::kByte).requires_grad(false));
+}
+
+void check_inputs(const Tensor &inputs, const Tensor &transition, int64_t T, int64_t N, int64_t L) {
+    check_cuda(inputs, "inputs");
+    check_cuda(transition, "transition");
+    TORCH_CHECK(inputs.dim() == 3 && inputs.size(0) == T && inputs.size(1) == N && inputs.size(2) == L,
+                "inputs must be [T,N,L] = [", T, ",", N, ",", L, "]");
+    TORCH_CHECK(transition.dim() == 2 && transition.size(0) == L && transition.size(1) == L, "transition must be [L,L]");
+    TORCH_CHECK(transition.scalar_type() == inputs.scalar_type(), "inputs and transition must share a dtype");
+    TORCH_CHECK(transition.device() == inputs.device(), "inputs and transition must share a device");
+}
+
+cudaStream_t current_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
+
+// ------------------------------------------------------------------------------------------------
+// reference: fully_connected_forward, fully_connected_lattice.h:41-49 / .cpp:66-91
+std::tuple<Tensor, Tensor, Tensor, Tensor> fully_connected_forward(Tensor &inputs, Tensor &transition,
+                                                                   Tensor &input_lengths, int64_t T, int64_t N, int64_t L) {
+    check_inputs(inputs, transition, T, N, L);
+    c10::cuda::CUDAGuard guard(inputs.device());
+    const int dt = dtype_code(inputs, "inputs");
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
+    const asg_layout_t lay = layout_of(dt, T, N, L, 1);
+    auto opt = inputs.options().requires_grad(false);
+    Tensor alpha = at::empty({T, N, L}, opt), beta = at::empty({T, N, L}, opt), scores = at::empty({N}, opt);
+    Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
+    check_rc(asg_scan(dt, ASG_ROLE_FCC_ALPHA | ASG_ROLE_FCC_BETA, inputs.data_ptr(), inputs.stride(0), inputs.stride(1),
+                      inputs.stride(2), transition.data_ptr(), transition.stride(0), transition.stride(1), nullptr, 0, 0,
+                      il.data_ptr<int64_t>(), nullptr, T, N, L, 1, alpha.data_ptr(), beta.data_ptr(), nullptr, nullptr,
+                      ctx.data_ptr(), scores.data_ptr(), nullptr, current_stream()));
+    return {scores, alpha, beta, ctx};
+}
+
+// reference: fully_connected_backward, fully_connected_lattice.h:51-60 / .cpp:94-104
+std::tuple<Tensor, Tensor> fully_connected_backward(Tensor &grad_out, Tensor &alpha, Tensor &beta, Tensor &path_contrib,
+                                                    int64_t T, int64_t N, int64_t L) {
+    check_cuda(alpha, "alpha");
+    c10::cuda::CUDAGuard guard(alpha.device());
+    const int dt = dtype_code(alpha, "alpha");
+    const asg_layout_t lay = layout_of(dt, T, N, L, 1);
+    TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
+                "path_contrib is not a context blob produced by this extension's fully_connected_forward");
+    Tensor g = grad_out.to(alpha.options());
+    auto opt = alpha.options().requires_grad(false);
+    Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
+    Tensor scratch = bytes_like(alpha, lay.grad_scratch_bytes);
+    check_rc(asg_grad(dt, ASG_PART_FCC, g.data_ptr(), g.dim() ? g.stride(0) : 0, nullptr, 0, alpha.data_ptr(), beta.data_ptr(),
+                      nullptr, nullptr, path_contrib.data_ptr(), nullptr, 0, 0, T, N, L, 1, grad_x.data_ptr(), grad_A.data_ptr(),
+                      scratch.data_ptr(), current_stream()));
+    return {grad_A, grad_x};
+}
+
+// reference: force_aligned_forward, force_aligned_lattice.h:42-53 / .cpp:266-319
+std::tuple<Tensor, Tensor, Tensor, Tensor> force_aligned_forward(Tensor &inputs, Tensor &targets, Tensor &transition,
+                                                                 Tensor &input_lengths, Tensor &target_lengths, int64_t T,
+                                                                 int64_t N, int64_t L, int64_t S) {
+    check_inputs(inputs, transition, T, N, L);
+    c10::cuda::CUDAGuard guard(inputs.device());
+    const int dt = dtype_code(inputs, "inputs");
+    Tensor y = as_device_long(targets, inputs, "targets");
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths");
+    TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
+    const asg_layout_t lay = layout_of(dt, T, N, L, S);
+    auto opt = inputs.options().requires_grad(false);
+    Tensor alpha = at::empty({T, N, lay.sp}, opt), beta = at::empty({T, N, lay.sp}, opt), scores = at::empty({N}, opt);
+    Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
+    check_rc(asg_scan(dt, ASG_ROLE_FAC_ALPHA | ASG_ROLE_FAC_BETA, inputs.data_ptr(), inputs.stride(0), inputs.stride(1),
+                      inputs.stride(2), transition.data_ptr(), transition.stride(0), transition.stride(1),
+                      y.data_ptr<int64_t>(), y.stride(0), y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L,
+                      S, nullptr, nullptr, alpha.data_ptr(), beta.data_ptr(), ctx.data_ptr(), nullptr, scores.data_ptr(),
+                      current_stream()));
+    return {scores, alpha.narrow(2, 0, S), beta.narrow(2, 0, S), ctx};
+}
+
+// reference: force_aligned_backward, force_aligned_lattice.h:56-69 / .cpp:321-356
+std::tuple<Tensor, Tensor> force_aligned_backward(Tensor &grad_out, Tensor &alpha, Tensor &beta, Tensor &path_contrib,
+                                                  Tensor &targets, Tensor &input_lengths, Tensor &target_lengths, int64_t T,
+                                                  int64_t N, int64_t L, int64_t S) {
+    check_cuda(alpha, "alpha");
+    c10::cuda::CUDAGuard guard(alpha.device());
+    const int dt = dtype_code(alpha, "alpha");
+    const asg_layout_t lay = layout_of(dt, T, N, L, S);
+    TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
+                "path_contrib is not a context blob produced by this extension's force_aligned_forward");
+    TORCH_CHECK(alpha.stride(1) == lay.sp && beta.stride(1) == lay.sp && alpha.stride(2) == 1,
+                "alpha/beta are not the state tensors produced by this extension's force_aligned_forward");
+    Tensor y = as_device_long(targets, alpha, "targets");
+    Tensor g = grad_out.to(alpha.options());
+    auto opt = alpha.options().requires_grad(false);
+    Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
+    Tensor scratch = bytes_like(alpha, lay.grad_scratch_bytes);
+    check_rc(asg_grad(dt, ASG_PART_FAC, nullptr, 0, g.data_ptr(), g.dim() ? g.stride(0) : 0, nullptr, nullptr, alpha.data_ptr(),
+                      beta.data_ptr(), path_contrib.data_ptr(), y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S,
+                      grad_x.data_ptr(), grad_A.data_ptr(), scratch.data_ptr(), current_stream()));
+    return {grad_A, grad_x};
+}
+
+// reference: fast_asg_gpu_forward_only, streamlined_fast_gpu.h:17-28 / .cpp:24-94
+Tensor fast_asg_gpu_forward_only(Tensor &inputs, Tensor &targets, Tensor &transition, Tensor &input_lengths,
+                                 Tensor &target_lengths, int64_t T, int64_t N, int64_t L, int64_t S) {
+    check_inputs(inputs, transition, T, N, L);
+    c10::cuda::CUDAGuard guard(inputs.device());
+    const int dt = dtype_code(inputs, "inputs");
+    Tensor y = as_device_long(targets, inputs, "targets");
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths");
+    const asg_layout_t lay = layout_of(dt, T, N, L, S);
+    auto opt = inputs.options().requires_grad(false);
+    Tensor full = at::empty({N}, opt), aligned = at::empty({N}, opt);
+    // forward-only keeps no state: only the small head of the context blob (E, lengths, scalars) is touched,
+    // but the offsets are those of the full layout, so the blob is allocated whole (uninitialised, untouched).
+    Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
+    check_rc(asg_scan(dt, ASG_ROLE_FORWARD_ONLY, inputs.data_ptr(), inputs.stride(0), inputs.stride(1), inputs.stride(2),
+                      transition.data_ptr(), transition.stride(0), transition.stride(1), y.data_ptr<int64_t>(), y.stride(0),
+                      y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, nullptr, nullptr, nullptr,
+                      nullptr, ctx.data_ptr(), full.data_ptr(), aligned.data_ptr(), current_stream()));
+    return full - aligned;
+}
+
+// reference: fast_asg_gpu_forward, streamlined_fast_gpu.h:30-48 / .cpp:104-230
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fast_asg_gpu_forward(Tensor &inputs, Tensor &targets,
+                                                                                Tensor &transition, Tensor &input_lengths,
+                                                                                Tensor &target_lengths, int64_t T, int64_t N,
+                                                                                int64_t L, int64_t S) {
+    check_inputs(inputs, transition, T, N, L);
+    c10::cuda::CUDAGuard guard(inputs.device());
+    const int dt = dtype_code(inputs, "inputs");
+    Tensor y = as_device_long(targets, inputs, "targets");
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths");
+    TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
+    const asg_layout_t lay = layout_of(dt, T, N, L, S);
+    auto opt = inputs.options().requires_grad(false);
+    Tensor full = at::empty({N}, opt), aligned = at::empty({N}, opt);
+    Tensor fcc_alpha = at::empty({T, N, L}, opt);
+    Tensor fac_alpha = at::empty({T, N, lay.sp}, opt);
+    // the two beta states travel in one opaque tensor (the "aligned_path_contrib" slot)
+    const size_t fb = (lay.fcc_state_bytes + 255) / 256 * 256;
+    Tensor betas = bytes_like(inputs, fb + lay.fac_state_bytes);
+    Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
+    char *bp = static_cast<char *>(betas.data_ptr());
+    check_rc(asg_scan(dt, ASG_ROLE_ALL, inputs.data_ptr(), inputs.stride(0), inputs.stride(1), inputs.stride(2),
+                      transition.data_ptr(), transition.stride(0), transition.stride(1), y.data_ptr<int64_t>(), y.stride(0),
+                      y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, fcc_alpha.data_ptr(), bp,
+                      fac_alpha.data_ptr(), bp + fb, ctx.data_ptr(), full.data_ptr(), aligned.data_ptr(), current_stream()));
+    return {full, aligned, fcc_alpha, fac_alpha.narrow(2, 0, S), ctx, betas};
+}
+
+// reference: fast_asg_gpu_backward, streamlined_fast_gpu.h:50-68 / .cpp:236-297
+std::tuple<Tensor, Tensor> fast_asg_gpu_backward(Tensor &grad_full, Tensor &grad_aligned, Tensor &full_gamma,
+                                                 Tensor &aligned_gamma, Tensor &full_path_contrib,
+                                                 Tensor &aligned_path_contrib, Tensor &targets, Tensor &input_lengths,
+                                                 Tensor &target_lengths, int64_t T, int64_t N, int64_t L, int64_t S) {
+    check_cuda(full_gamma, "full_gamma");
+    c10::cuda::CUDAGuard guard(full_gamma.device());
+    const int dt = dtype_code(full_gamma, "full_gamma");
+    const asg_layout_t lay = layout_of(dt, T, N, L, S);
+    const size_t fb = (lay.fcc_state_bytes + 255) / 256 * 256;
+    TORCH_CHECK((size_t)full_path_contrib.numel() == lay.ctx_bytes && full_path_contrib.scalar_type() == at::kByte &&
+                    (size_t)aligned_path_contrib.numel() == fb + lay.fac_state_bytes &&
+                    aligned_gamma.stride(1) == lay.sp && full_gamma.is_contiguous(),
+                "saved tensors were not produced by this extension's fast_asg_gpu_forward");
+    Tensor y = as_device_long(targets, full_gamma, "targets");
+    Tensor gf = grad_full.to(full_gamma.options()), ga = grad_aligned.to(full_gamma.options());
+    auto opt = full_gamma.options().requires_grad(false);
+    Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
+    Tensor scratch = bytes_like(full_gamma, lay.grad_scratch_bytes);
+    char *bp = static_cast<char *>(aligned_path_contrib.data_ptr());
+    check_rc(asg_grad(dt, ASG_PART_BOTH, gf.data_ptr(), gf.dim() ? gf.stride(0) : 0, ga.data_ptr(), ga.dim() ? ga.stride(0) : 0,
+                      full_gamma.data_ptr(), bp, aligned_gamma.data_ptr(), bp + fb, full_path_contrib.data_ptr(),
+                      y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S, grad_x.data_ptr(), grad_A.data_ptr(),
+                      scratch.data_ptr(), current_stream()));
+    return {grad_A, grad_x};
+}
+
+// ---- extras (not in the reference): introspection for tests and bench.py ------------------------
+Tensor ctx_scalars(Tensor &ctx, bool is_double, int64_t T, int64_t N, int64_t L, int64_t S) {
+    const asg_layout_t lay = layout_of(is_double ? ASG_F64 : ASG_F32, T, N, L, S);
+    TORCH_CHECK((size_t)ctx.numel() == lay.ctx_bytes, "not a context blob for these dimensions");
+    Tensor view = at::from_blob(static_cast<char *>(ctx.data_ptr()) + lay.off_scalars, {N, 8},
+                                ctx.options().dtype(at::kDouble));
+    return view.clone();
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "torch_asg_native -- B200 (sm_100a) implementation of zh217/torch-asg's native boundary";
+    m.def("fully_connected_forward", &fully_connected_forward, "fully-connected forward");
+    m.def("fully_connected_backward", &fully_connected_backward, "fully-connected backward");
+    m.def("force_aligned_forward", &force_aligned_forward, "force-aligned forward");
+    m.def("force_aligned_backward", &force_aligned_backward, "force-aligned backward");
+    m.def("fast_asg_gpu_forward_only", &fast_asg_gpu_forward_only, "fast ASG GPU forward only");
+    m.def("fast_asg_gpu_forward", &fast_asg_gpu_forward, "fast ASG GPU forward");
+    m.def("fast_asg_gpu_backward", &fast_asg_gpu_backward, "fast ASG GPU backward");
+    m.def("_ctx_scalars", &ctx_scalars, "per-utterance float64 bookkeeping [N,8] of a context blob");
+    m.def("_launch_count", []() { return asg_launch_count(); }, "kernels launched by libasg_b200 so far");
+    m.def("_version", []() { return std::string(asg_version()); });
+    m.attr("IS_B200_BUILD") = true;
+}
