@@ -158,6 +158,19 @@ const char *asg_version(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t asg_launch_count(void);
 
+/*
+ * Live per-kernel timing (bench.py's roofline leg).  While enabled, every kernel this library launches is
+ * bracketed by a pair of CUDA events recorded on the stream it is launched on; asg_profile_read() waits for
+ * the recorded events and returns the accumulated device time and launch count of one kernel id
+ * (0 <= id < asg_kernel_count(); asg_kernel_name(id) names it).  No reference counterpart: the reference
+ * has no timers.
+ */
+int asg_profile_enable(int on);
+int asg_profile_reset(void);
+int asg_profile_read(int kernel_id, double *total_ms, uint64_t *launches);
+const char *asg_kernel_name(int kernel_id);
+int asg_kernel_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,98 @@
+"""CPU tier: the C-ABI shared library loads without a GPU and exports every symbol that
+include/asg_b200.h declares; argument validation works; compute entry points refuse to run without a
+device (there is no CPU fallback).  No kernels are launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HEADER = os.path.join(ROOT, "include", "asg_b200.h")
+LIB = os.path.join(ROOT, "torch-asg_b200", "libasg_b200.so")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(asg_[a-z_0-9]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(LIB)
+    lib.asg_last_error.restype = ctypes.c_char_p
+    lib.asg_version.restype = ctypes.c_char_p
+    lib.asg_kernel_name.restype = ctypes.c_char_p
+    return lib
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert {"asg_layout", "asg_scan", "asg_grad", "asg_host_create", "asg_host_destroy", "asg_host_loss",
+            "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_read"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), "libasg_b200.so does not export " + n
+    assert b"sm_100a" in lib.asg_version()
+
+
+def test_sass_is_sm_100a_only():
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+class Layout(ctypes.Structure):
+    _fields_ = [("sp", ctypes.c_int64), ("nblk", ctypes.c_int64)] + [
+        (n, ctypes.c_size_t) for n in ("elem_bytes", "fcc_state_bytes", "fac_state_bytes", "ctx_bytes",
+                                       "grad_scratch_bytes", "off_ehat", "off_fcc_scale", "off_fcc_w", "off_fac_hd",
+                                       "off_fac_ea", "off_fac_eb", "off_lengths", "off_scalars")]
+
+
+def _layout(lib, dt, T, N, L, S):
+    lay = Layout()
+    rc = lib.asg_layout(dt, ctypes.c_int64(T), ctypes.c_int64(N), ctypes.c_int64(L), ctypes.c_int64(S), ctypes.byref(lay))
+    return rc, lay
+
+
+def test_layout_and_validation(lib):
+    rc, lay = _layout(lib, 0, 1000, 64, 40, 200)
+    assert rc == 0
+    assert lay.sp == 200 and lay.nblk == 25 and lay.elem_bytes == 4
+    assert lay.fcc_state_bytes == 4 * 1000 * 64 * 40
+    assert lay.fac_state_bytes == 4 * 1000 * 64 * 200
+    offs = [lay.off_ehat, lay.off_fcc_scale, lay.off_fcc_w, lay.off_fac_hd, lay.off_fac_ea, lay.off_fac_eb,
+            lay.off_lengths, lay.off_scalars]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.ctx_bytes > offs[-1]
+    rc, lay = _layout(lib, 1, 7, 3, 5, 3)
+    assert rc == 0 and lay.sp == 8 and lay.elem_bytes == 8
+    assert _layout(lib, 5, 4, 1, 3, 2)[0] == -1 and b"dtype" in lib.asg_last_error()
+    assert _layout(lib, 0, 4, 1, 3, 5)[0] == -2          # S > T
+    assert _layout(lib, 0, 4, 0, 3, 2)[0] == -2
+    assert lib.asg_layout(0, ctypes.c_int64(4), ctypes.c_int64(1), ctypes.c_int64(3), ctypes.c_int64(2), None) == -3
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less box")
+    h = ctypes.c_void_p()
+    rc = lib.asg_host_create(0, 0, ctypes.c_int64(8), ctypes.c_int64(1), ctypes.c_int64(4), ctypes.c_int64(2), ctypes.byref(h))
+    assert rc == -5 and b"no CPU fallback" in lib.asg_last_error()
+    import torch_asg_native as nat
+    x = torch.zeros(4, 2, 3)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        nat.fully_connected_forward(x, torch.zeros(3, 3), torch.full((2,), 4), 4, 2, 3)
+    from torch_asg import ASGLoss
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ASGLoss(3)(x, torch.zeros(2, 2, dtype=torch.long))
+
+
+def test_kernel_names(lib):
+    n = lib.asg_kernel_count()
+    names = [lib.asg_kernel_name(i).decode() for i in range(n)]
+    assert "grad_kernel" in names and "fcc_scan_kernel" in names and "fac_scan_kernel" in names

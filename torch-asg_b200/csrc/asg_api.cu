@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 #include "asg_common.cuh"
 #include "asg_internal.h"
 
@@ -13,6 +15,52 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- live profiler: CUDA-event pairs around every launch, on the launching stream ---------------
+namespace {
+constexpr int PROF_SLOTS = 8192;
+struct ProfRec { cudaEvent_t a, b; int kid; };
+std::mutex g_prof_mu;
+std::atomic<int> g_prof_on{0};
+std::vector<ProfRec> g_prof_recs;       // recorded since the last read
+std::vector<ProfRec> g_prof_free;       // recycled event pairs
+double g_prof_ms[K_COUNT] = {0};
+uint64_t g_prof_n[K_COUNT] = {0};
+std::atomic<uint64_t> g_kid_launches[K_COUNT];
+}  // namespace
+
+LaunchScope::LaunchScope(int kid, cudaStream_t st) : kid_(kid), st_(st), slot_(-1) {
+    count_launch();
+    g_kid_launches[kid].fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if ((int)g_prof_recs.size() >= PROF_SLOTS) return;
+    ProfRec r;
+    if (!g_prof_free.empty()) { r = g_prof_free.back(); g_prof_free.pop_back(); }
+    else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    r.kid = kid;
+    cudaEventRecord(r.a, st);
+    g_prof_recs.push_back(r);
+    slot_ = (int)g_prof_recs.size() - 1;
+}
+LaunchScope::~LaunchScope() {
+    if (slot_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot_ < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot_].b, st_);
+}
+
+static void prof_drain() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_prof_ms[r.kid] += ms;
+            g_prof_n[r.kid] += 1;
+        }
+        g_prof_free.push_back(r);
+    }
+    g_prof_recs.clear();
+}
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -253,12 +301,12 @@ int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t
     const int nb = (int)((N + 127) / 128);
     if (h->dtype == ASG_F32) host_loss_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_full), (float *)(d + h->o_al), (float *)(d + h->o_loss), (int)N);
     else host_loss_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_full), (double *)(d + h->o_al), (double *)(d + h->o_loss), (int)N);
-    count_launch();
+    { LaunchScope ls(K_HOST_MISC, st); }
     ASG_TRY(cudaMemcpyAsync(loss, d + h->o_loss, eb * (size_t)N, cudaMemcpyDeviceToHost, st), "D2H loss");
     if (want_grad) {
         if (h->dtype == ASG_F32) host_g_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_g), (float *)(d + h->o_g), (float *)(d + h->o_gneg), (int)N, g != nullptr);
         else host_g_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_g), (double *)(d + h->o_g), (double *)(d + h->o_gneg), (int)N, g != nullptr);
-        count_launch();
+        { LaunchScope ls(K_HOST_MISC, st); }
         rc = asg_grad(h->dtype, ASG_PART_BOTH, d + h->o_g, 1, d + h->o_gneg, 1, d + h->o_fa, d + h->o_fb, d + h->o_aa,
                       d + h->o_ab, d + h->o_ctx, (const int64_t *)(d + h->o_y), S, 1, T, N, L, S, d + h->o_gx, d + h->o_gA,
                       d + h->o_scr, st);
@@ -274,5 +322,30 @@ int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t
 const char *asg_last_error(void) { return g_err; }
 const char *asg_version(void) { return "asg_b200 0.1 (sm_100a)"; }
 uint64_t asg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int asg_profile_enable(int on) {
+    if (!on) prof_drain();
+    g_prof_on.store(on ? 1 : 0);
+    return 0;
+}
+int asg_profile_reset(void) {
+    prof_drain();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int k = 0; k < K_COUNT; ++k) { g_prof_ms[k] = 0; g_prof_n[k] = 0; }
+    return 0;
+}
+int asg_profile_read(int kernel_id, double *total_ms, uint64_t *launches) {
+    if (kernel_id < 0 || kernel_id >= K_COUNT) return fail(ASG_E_SHAPE, "asg_profile_read: bad kernel id %d", kernel_id);
+    prof_drain();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (total_ms) *total_ms = g_prof_ms[kernel_id];
+    if (launches) *launches = g_prof_n[kernel_id];
+    return 0;
+}
+const char *asg_kernel_name(int kernel_id) {
+    static const char *names[K_COUNT] = {"fcc_scan_kernel", "fac_scan_kernel", "grad_kernel", "grad_finalize_kernel", "host_misc"};
+    return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "";
+}
+int asg_kernel_count(void) { return K_COUNT; }
 
 }  // extern "C"

@@ -406,12 +406,16 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     int grid = grad_grid_size(device);
     if (grid > a.num_tiles) grid = a.num_tiles;
-    grad_kernel<T, LP, FCC, FAC><<<grid, GRAD_THREADS, bytes, st>>>(a);
-    count_launch();
+    {
+        LaunchScope ls(K_GRAD, st);
+        grad_kernel<T, LP, FCC, FAC><<<grid, GRAD_THREADS, bytes, st>>>(a);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const int LL = L * L;
-    grad_finalize_kernel<T><<<(LL + 255) / 256, 256, 0, st>>>(a.partials, grid, LL, a.grad_A);
-    count_launch();
+    {
+        LaunchScope ls(K_GRAD_FINALIZE, st);
+        grad_finalize_kernel<T><<<(LL + 255) / 256, 256, 0, st>>>(a.partials, grid, LL, a.grad_A);
+    }
     return cudaGetLastError();
 }
 

@@ -78,4 +78,15 @@ template <typename T> int launch_grad(const GradArgs<T> &a, int parts, cudaStrea
 int grad_grid_size(int device);   // number of persistent CTAs asg_grad launches
 void count_launch(int n = 1);
 
+// kernel ids for the launch counter / live profiler (asg_profile_* in include/asg_b200.h)
+enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_COUNT = 5 };
+
+// RAII: counts one launch of kernel `kid` and, while profiling is enabled, brackets it with a pair
+// of CUDA events recorded on the launching stream (read back by asg_profile_read()).
+struct LaunchScope {
+    LaunchScope(int kid, cudaStream_t st);
+    ~LaunchScope();
+    int kid_; cudaStream_t st_; int slot_;
+};
+
 }  // namespace asg

@@ -594,8 +594,10 @@ static cudaEvent_t pooled_event(int device, int which) {
 template <typename T, int LP>
 static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
     dim3 grid(a.d.N, nroles);
-    fcc_scan_kernel<T, LP><<<grid, 64, 0, st>>>(a);
-    count_launch();
+    {
+        LaunchScope ls(K_FCC_SCAN, st);
+        fcc_scan_kernel<T, LP><<<grid, 64, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -622,8 +624,10 @@ static cudaError_t launch_fac_w(const ScanArgs<T> &a, int nroles, cudaStream_t s
     cudaError_t e = cudaFuncSetAttribute(fac_scan_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     dim3 grid(a.d.N, nroles);
-    fac_scan_kernel<T, W><<<grid, 32 * W + 32, bytes, st>>>(a, D);
-    count_launch();
+    {
+        LaunchScope ls(K_FAC_SCAN, st);
+        fac_scan_kernel<T, W><<<grid, 32 * W + 32, bytes, st>>>(a, D);
+    }
     return cudaGetLastError();
 }
 

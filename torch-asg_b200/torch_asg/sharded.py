@@ -1,0 +1,87 @@
+"""Batch-sharded ASG over the GPUs of one box (one process per GPU, ``torch.distributed``).
+
+Utterances are independent: rank ``r`` owns a contiguous slice of the batch, runs the whole
+path (four scans + gradient assembly) on it, and the only cross-rank quantities are sums over utterances --
+the transition gradient ``gA[L,L]`` (reference: the ``.sum({0,1})`` of ``fully_connected_lattice.cpp:60`` and
+the scatter of ``force_aligned_lattice.cpp:220-230`` both run over the batch) and the reduced loss
+(``asg.py:137-140``).  They travel in ONE all-reduce of a fused ``[L*L + 2]`` buffer
+(``gA``, ``sum of finite losses``, ``count of utterances``); ``grad_inputs`` never leaves its rank (it feeds
+that rank's acoustic model).  There is no other data-path collective.
+
+The reference itself has no distributed code; this is the B200-side answer to BASELINE.json's
+"Batch-sharded" config.  The arithmetic lives in the CUDA extension; this file is host plumbing only and
+is exercised on CPU by ``tests/test_sharded_gloo.py`` (world_size 2, ``gloo``) with a stand-in compute
+function.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(batch, world_size, rank):
+    """Contiguous, balanced split of ``batch`` utterances: the first ``batch % world_size`` ranks get one
+    extra.  Returns ``(begin, end)``."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    base, extra = divmod(batch, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_batch(inputs, targets, input_lengths, target_lengths, world_size, rank):
+    """Views (no copies) of this rank's utterances: ``inputs[:, b:e, :]`` is a strided view -- the
+    kernels take strides -- and ``targets[b:e]`` / lengths are row slices."""
+    b, e = shard_bounds(inputs.shape[1], world_size, rank)
+    il = None if input_lengths is None else input_lengths[b:e]
+    tl = None if target_lengths is None else target_lengths[b:e]
+    return inputs[:, b:e, :], targets[b:e], il, tl
+
+
+def pack_for_allreduce(grad_transition, loss_sum, count):
+    """Fused buffer ``[L*L + 2]`` in the gradient's dtype: gA (flattened), local loss sum, local count."""
+    flat = grad_transition.reshape(-1)
+    buf = flat.new_empty(flat.numel() + 2)
+    buf[:-2].copy_(flat)
+    buf[-2] = loss_sum
+    buf[-1] = count
+    return buf
+
+
+def unpack_after_allreduce(buf, num_labels):
+    return buf[:-2].view(num_labels, num_labels), buf[-2], buf[-1]
+
+
+def sharded_asg_step(criterion, inputs, targets, input_lengths=None, target_lengths=None, group=None,
+                     global_batch=None):
+    """One forward+backward of ``criterion`` (an ``ASGLoss`` whose ``reduction`` is honoured GLOBALLY) on
+    this rank's utterances, followed by the single fused all-reduce.
+
+    ``inputs`` must be a leaf that requires grad (or feed from a graph that does).  On return:
+    ``criterion.transition.grad`` holds the global transition gradient on every rank, ``inputs.grad`` the
+    local input gradient (already scaled for the global reduction), and the returned scalar is the global
+    reduced loss.  With ``reduction='mean'`` the upstream gradient is ``1/global_batch`` (not ``1/local``).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_local = inputs.shape[1]
+    if global_batch is None:
+        global_batch = n_local * world
+    reduction = criterion.reduction
+    saved = criterion.reduction
+    criterion.reduction = 'none'
+    try:
+        per_utt = criterion(inputs, targets, input_lengths, target_lengths)
+    finally:
+        criterion.reduction = saved
+    local_sum = per_utt.sum()
+    scale = 1.0 / global_batch if reduction == 'mean' else 1.0
+    if criterion.transition.grad is not None:
+        criterion.transition.grad = None
+    (local_sum * scale).backward()
+    gA = criterion.transition.grad
+    buf = pack_for_allreduce(gA, local_sum.detach(), float(n_local))
+    if world > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    gA_glob, loss_sum, count = unpack_after_allreduce(buf, gA.shape[0])
+    criterion.transition.grad = gA_glob.clone()
+    if reduction == 'mean':
+        return loss_sum / count
+    return loss_sum
