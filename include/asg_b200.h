@@ -71,23 +71,31 @@ enum {
     ASG_E_NOGPU = -5    /* no CUDA device / driver: there is no CPU fallback */
 };
 
-/* Sizes and offsets of the opaque buffers a caller allocates for one (dtype,T,N,L,S) problem. */
+/*
+ * Sizes and offsets of the opaque buffers a caller allocates for one (dtype,T,N,L,S) problem.
+ * All state is UTTERANCE-MAJOR ([N, tp, ...]): one utterance's frames are contiguous, so the serial scans write
+ * one sequential stream each and the gradient assembly fetches a (utterance, frame-range) tile with a handful of
+ * contiguous bulk (TMA) copies.  Row pitches are padded so every tile starts 16-byte aligned.
+ */
 typedef struct asg_layout {
     int64_t sp;               /* row pitch (elements) of the FAC state arrays: S rounded up to 8 */
     int64_t nblk;             /* block exponents per (frame, utterance): sp / 8 */
+    int64_t nbp;              /* row pitch of the exponent arrays: nblk rounded up to 4 */
+    int64_t lpi;              /* row pitch of the FCC state arrays: L rounded up to 4 */
+    int64_t tp;               /* frame pitch: T rounded up to 4 */
     size_t elem_bytes;        /* 4 or 8 */
-    size_t fcc_state_bytes;   /* one FCC state array  [T,N,L]   */
-    size_t fac_state_bytes;   /* one FAC state array  [T,N,sp]  */
+    size_t fcc_state_bytes;   /* one FCC state array  [N,tp,lpi]  */
+    size_t fac_state_bytes;   /* one FAC state array  [N,tp,sp]   */
     size_t ctx_bytes;         /* the context blob handed from asg_scan() to asg_grad() */
     size_t grad_scratch_bytes;/* scratch for asg_grad() (per-CTA partial sums) */
     /* byte offsets inside the context blob (all 256-byte aligned) */
-    size_t off_ehat;          /* [L,L]     exp(A - R)                         */
-    size_t off_fcc_scale;     /* [T,N]     power-of-two applied to alpha at frame t */
-    size_t off_fcc_w;         /* [T,N,L]   u_t * beta_t (emission-weighted beta)    */
-    size_t off_fac_hd;        /* [2,N,sp]  exp(H - Rb), exp(D - Rb)           */
-    size_t off_fac_ea;        /* [T,N,nblk] int32 block exponents of FAC alpha */
-    size_t off_fac_eb;        /* [T,N,nblk] int32 block exponents of FAC beta  */
-    size_t off_lengths;       /* [2,N] int64 copies of il, tl                 */
+    size_t off_ehat;          /* [L,L]       exp(A - R)                              */
+    size_t off_fcc_scale;     /* [N,tp]      power-of-two applied to alpha at frame t */
+    size_t off_fcc_w;         /* [N,tp,lpi]  u_t * beta_t (emission-weighted beta)     */
+    size_t off_fac_hd;        /* [2,N,sp]    exp(H - Rb), exp(D - Rb)                */
+    size_t off_fac_ea;        /* [N,tp,nbp]  int32 block exponents of FAC alpha      */
+    size_t off_fac_eb;        /* [N,tp,nbp]  int32 block exponents of FAC beta       */
+    size_t off_lengths;       /* [2,N] int64 copies of il, tl                        */
     size_t off_scalars;       /* [N,8] float64: per-utterance log-scale bookkeeping (scores in f64 etc.) */
 } asg_layout_t;
 
@@ -98,8 +106,8 @@ int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout
  * Forward recursions.  Outputs whose role is not selected may be NULL.  fcc_beta / fac_beta may also be
  * NULL when their role IS selected: the beta scans then only produce the scores (forward-only mode,
  * nothing is stored -- fast_asg_gpu_forward_only, streamlined_fast_gpu.cpp:24-94).
- *   fcc_alpha, fcc_beta : [T,N,L]   device, dtype
- *   fac_alpha, fac_beta : [T,N,sp]  device, dtype
+ *   fcc_alpha, fcc_beta : [N,tp,lpi] device, dtype (asg_layout_t.fcc_state_bytes each)
+ *   fac_alpha, fac_beta : [N,tp,sp]  device, dtype (asg_layout_t.fac_state_bytes each)
  *   ctx                 : ctx_bytes device (always required)
  *   full_scores         : [N] dtype, written when ASG_ROLE_FCC_BETA is selected
  *   aligned_scores      : [N] dtype, written when ASG_ROLE_FAC_BETA is selected

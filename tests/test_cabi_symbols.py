@@ -47,7 +47,7 @@ def test_sass_is_sm_100a_only():
 
 
 class Layout(ctypes.Structure):
-    _fields_ = [("sp", ctypes.c_int64), ("nblk", ctypes.c_int64)] + [
+    _fields_ = [(n, ctypes.c_int64) for n in ("sp", "nblk", "nbp", "lpi", "tp")] + [
         (n, ctypes.c_size_t) for n in ("elem_bytes", "fcc_state_bytes", "fac_state_bytes", "ctx_bytes",
                                        "grad_scratch_bytes", "off_ehat", "off_fcc_scale", "off_fcc_w", "off_fac_hd",
                                        "off_fac_ea", "off_fac_eb", "off_lengths", "off_scalars")]
@@ -62,14 +62,14 @@ def _layout(lib, dt, T, N, L, S):
 def test_layout_and_validation(lib):
     rc, lay = _layout(lib, 0, 1000, 64, 40, 200)
     assert rc == 0
-    assert lay.sp == 200 and lay.nblk == 25 and lay.elem_bytes == 4
+    assert (lay.sp, lay.nblk, lay.nbp, lay.lpi, lay.tp, lay.elem_bytes) == (200, 25, 28, 40, 1000, 4)
     assert lay.fcc_state_bytes == 4 * 1000 * 64 * 40
     assert lay.fac_state_bytes == 4 * 1000 * 64 * 200
     offs = [lay.off_ehat, lay.off_fcc_scale, lay.off_fcc_w, lay.off_fac_hd, lay.off_fac_ea, lay.off_fac_eb,
             lay.off_lengths, lay.off_scalars]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.ctx_bytes > offs[-1]
     rc, lay = _layout(lib, 1, 7, 3, 5, 3)
-    assert rc == 0 and lay.sp == 8 and lay.elem_bytes == 8
+    assert rc == 0 and (lay.sp, lay.nblk, lay.nbp, lay.lpi, lay.tp, lay.elem_bytes) == (8, 1, 4, 8, 8, 8)
     assert _layout(lib, 5, 4, 1, 3, 2)[0] == -1 and b"dtype" in lib.asg_last_error()
     assert _layout(lib, 0, 4, 1, 3, 5)[0] == -2          # S > T
     assert _layout(lib, 0, 4, 0, 3, 2)[0] == -2

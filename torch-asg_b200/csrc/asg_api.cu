@@ -106,7 +106,7 @@ static int scan_typed(int roles, const void *x, int64_t x_st, int64_t x_sn, int6
     a.fac_alpha = (T *)fac_alpha; a.fac_beta = (T *)fac_beta;
     a.ctx = make_ctx<T>(ctx, lay, N);
     a.full_scores = (T *)full_scores; a.aligned_scores = (T *)aligned_scores;
-    a.role0 = a.role1 = 0;
+    a.dir0 = a.dir1 = 0; a.fcc_dirs = a.fac_dirs = 0;
     return launch_scan<T>(a, roles, stream);
 }
 
@@ -160,16 +160,20 @@ int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout
     out->elem_bytes = eb;
     out->sp = (S + ASG_BLK - 1) / ASG_BLK * ASG_BLK;
     out->nblk = out->sp / ASG_BLK;
-    out->fcc_state_bytes = eb * (size_t)T * N * L;
-    out->fac_state_bytes = eb * (size_t)T * N * out->sp;
+    out->nbp = (out->nblk + 3) / 4 * 4;
+    out->lpi = (L + 3) / 4 * 4;
+    out->tp = (T + 3) / 4 * 4;
+    const size_t NT = (size_t)N * out->tp;
+    out->fcc_state_bytes = eb * NT * out->lpi;
+    out->fac_state_bytes = eb * NT * out->sp;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     out->off_ehat = take(eb * (size_t)L * L);
-    out->off_fcc_scale = take(eb * (size_t)T * N);
-    out->off_fcc_w = take(eb * (size_t)T * N * L);
+    out->off_fcc_scale = take(eb * NT);
+    out->off_fcc_w = take(eb * NT * out->lpi);
     out->off_fac_hd = take(eb * 2 * (size_t)N * out->sp);
-    out->off_fac_ea = take(sizeof(int) * (size_t)T * N * out->nblk);
-    out->off_fac_eb = take(sizeof(int) * (size_t)T * N * out->nblk);
+    out->off_fac_ea = take(sizeof(int) * NT * out->nbp);
+    out->off_fac_eb = take(sizeof(int) * NT * out->nbp);
     out->off_lengths = take(sizeof(int64_t) * 2 * (size_t)N);
     out->off_scalars = take(sizeof(double) * 8 * (size_t)N);
     out->ctx_bytes = off;

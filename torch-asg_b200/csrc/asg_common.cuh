@@ -92,6 +92,36 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk (TMA, non-tensor) copies: cp.async.bulk -> SASS UBLKCP, expect_tx -> SYNCS.ARRIVE.TRANS64
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    const unsigned addr = smem_u32(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// orders this thread's generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // volatile shared-memory progress counters (producer/consumer rings)
 __device__ __forceinline__ int ld_volatile_s32(const int *p) {
     int v;
@@ -111,6 +141,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // streaming (evict-first) global stores for state arrays that are written once and read once later
 template <typename T> __device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+
+// 8 consecutive elements (32-byte aligned for float) through the streaming store path
+__device__ __forceinline__ void store8_stream(float *p, const float (&v)[8]) {
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    __stcs(reinterpret_cast<float4 *>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ void store8_stream(double *p, const double (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) __stcs(reinterpret_cast<double2 *>(p) + q, make_double2(v[2 * q], v[2 * q + 1]));
+}
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -98,7 +98,8 @@ template <typename T, int LP, bool FCC, bool FAC>
 __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a) {
     extern __shared__ __align__(16) char smem_raw[];
     const int L = a.d.L, N = a.d.N, Tt = a.d.T;
-    const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, spp = sp | 1;
+    const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp, lpi = (int)a.ctx.lpi, spp = sp | 1;
+    const int64_t tp = a.ctx.tp;
     const int TB = a.tb;
     GradSmem<T> sm;
     grad_smem_carve<T>(&sm, smem_raw, L, LP, sp, nblk, TB, FCC, FAC);
@@ -163,14 +164,22 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
                     sm.tD[s] = T(0);
                 }
                 __syncthreads();
-                // CSR by label; positions ascending inside a label (fixed summation order)
+                // CSR by label; positions ascending inside a label (fixed summation order).
+                // Thread l counts, thread 0 scans the L counts, thread l fills its own segment.
+                int cnt = 0;
+                if (tid < L)
+                    for (int s = 0; s < Sn; ++s) cnt += (sm.ylab[s] == tid);
+                if (tid < L) sm.lstart[tid + 1] = cnt;
+                __syncthreads();
                 if (tid == 0) {
                     int acc = 0;
-                    for (int l = 0; l < L; ++l) {
-                        sm.lstart[l] = acc;
-                        for (int s = 0; s < Sn; ++s) if (sm.ylab[s] == l) sm.order[acc++] = s;
-                    }
-                    sm.lstart[L] = acc;
+                    sm.lstart[0] = 0;
+                    for (int l = 0; l < L; ++l) { acc += sm.lstart[l + 1]; sm.lstart[l + 1] = acc; }
+                }
+                __syncthreads();
+                if (tid < L) {
+                    int pos = sm.lstart[tid];
+                    for (int s = 0; s < Sn; ++s) if (sm.ylab[s] == tid) sm.order[pos++] = s;
                 }
             }
             __syncthreads();
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
             const int t = t0 - 1 + r;
             const bool have_prev = (t >= 0) && (t < Tn);          // alpha row t exists
             const bool cur = (r >= 1) && (t < Tn);                // frame t is a live frame of this tile
-            const int64_t row = (int64_t)t * N + n;
+            const int64_t row = (int64_t)n * tp + t;
             if (FAC) {
                 T zsum = T(0);
                 int cmax = INT_MIN;
@@ -195,14 +204,14 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
                     int ea = 0, eb = 0;
                     if (have_prev) {
                         load8(a.fac_alpha + row * sp + (int64_t)b * 8, av);
-                        ea = __ldcs(a.ctx.fac_ea + row * nblk + b);
+                        ea = __ldcs(a.ctx.fac_ea + row * nbp + b);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) av[j] = T(0);
                     }
                     if (cur) {
                         load8(a.fac_beta + row * sp + (int64_t)b * 8, bv);
-                        eb = __ldcs(a.ctx.fac_eb + row * nblk + b);
+                        eb = __ldcs(a.ctx.fac_eb + row * nbp + b);
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) sm.sA[r * spp + b * 8 + j] = av[j];
@@ -244,18 +253,18 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
             if (FCC) {
                 T al0 = T(0), al1 = T(0);
                 if (have_prev) {
-                    if (lane < L) al0 = __ldcs(a.fcc_alpha + row * L + lane);
-                    if (LP > 32 && lane + 32 < L) al1 = __ldcs(a.fcc_alpha + row * L + lane + 32);
+                    if (lane < L) al0 = __ldcs(a.fcc_alpha + row * lpi + lane);
+                    if (LP > 32 && lane + 32 < L) al1 = __ldcs(a.fcc_alpha + row * lpi + lane + 32);
                 }
                 if (lane < LP) sm.sAl[r * LP + lane] = al0;
                 if (LP > 32 && lane + 32 < LP) sm.sAl[r * LP + lane + 32] = al1;
                 if (r >= 1) {
                     T be0 = T(0), be1 = T(0), w0 = T(0), w1 = T(0), sc = T(0);
                     if (cur) {
-                        if (lane < L) { be0 = __ldcs(a.fcc_beta + row * L + lane); w0 = __ldcs(a.ctx.fcc_w + row * L + lane); }
+                        if (lane < L) { be0 = __ldcs(a.fcc_beta + row * lpi + lane); w0 = __ldcs(a.ctx.fcc_w + row * lpi + lane); }
                         if (LP > 32 && lane + 32 < L) {
-                            be1 = __ldcs(a.fcc_beta + row * L + lane + 32);
-                            w1 = __ldcs(a.ctx.fcc_w + row * L + lane + 32);
+                            be1 = __ldcs(a.fcc_beta + row * lpi + lane + 32);
+                            w1 = __ldcs(a.ctx.fcc_w + row * lpi + lane + 32);
                         }
                         sc = __ldcs(a.ctx.fcc_scale + row);
                     }

@@ -9,15 +9,15 @@ namespace asg {
 // typed view of the context blob (see asg_layout_t)
 template <typename T> struct Ctx {
     T *ehat;          // [L,L]
-    T *fcc_scale;     // [T,N]
-    T *fcc_w;         // [T,N,L]
+    T *fcc_scale;     // [N,tp]
+    T *fcc_w;         // [N,tp,lpi]
     T *fac_hd;        // [2,N,sp]   h_s, d_s (edge s -> s+1)
-    int *fac_ea;      // [T,N,nblk]
-    int *fac_eb;      // [T,N,nblk]
+    int *fac_ea;      // [N,tp,nbp]
+    int *fac_eb;      // [N,tp,nbp]
     int64_t *il;      // [N]
     int64_t *tl;      // [N]
     double *scalars;  // [N,8]
-    int64_t sp, nblk;
+    int64_t sp, nblk, nbp, lpi, tp;
 };
 
 // per-utterance float64 bookkeeping slots in Ctx::scalars
@@ -38,6 +38,9 @@ template <typename T> inline Ctx<T> make_ctx(void *blob, const asg_layout_t &lay
     c.scalars = reinterpret_cast<double *>(b + lay.off_scalars);
     c.sp = lay.sp;
     c.nblk = lay.nblk;
+    c.nbp = lay.nbp;
+    c.lpi = lay.lpi;
+    c.tp = lay.tp;
     return c;
 }
 
@@ -51,11 +54,12 @@ template <typename T> struct ScanArgs {
     const int64_t *y; int64_t y_s0, y_s1;
     const int64_t *il, *tl;     // may be NULL
     Dims d;
-    T *fcc_alpha, *fcc_beta;    // [T,N,L]
-    T *fac_alpha, *fac_beta;    // [T,N,sp]
+    T *fcc_alpha, *fcc_beta;    // [N,tp,lpi]
+    T *fac_alpha, *fac_beta;    // [N,tp,sp]
     Ctx<T> ctx;
     T *full_scores, *aligned_scores;
-    int role0, role1;           // roles (0 = alpha, 1 = beta) served by blockIdx.y = 0 / 1
+    int dir0, dir1;             // direction (0 = alpha, 1 = beta) served by blockIdx.y = 0 / 1
+    int fcc_dirs, fac_dirs;     // bit d set: that lattice runs direction d
 };
 
 template <typename T> struct GradArgs {

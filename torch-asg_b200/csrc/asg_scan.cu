@@ -10,31 +10,108 @@
 // Shape of the computation: the T axis is strictly serial, so every (utterance, recursion) pair is
 // one latency-bound chain.  Each chain gets its own CTA: one (FCC) or W (FAC) *consumer* warps that do
 // nothing but the recurrence, fed by one *producer* warp that streams the utterance's emission rows
-// from HBM with a cp.async ring, turns them into per-frame-normalised exponentials u_t = exp(x_t - max x_t)
-// (and, for FAC, gathers them into target order) and publishes them through a shared-memory ring.
+// from HBM FB frames at a time (cp.async ring, NRAW batches in flight), turns each batch into
+// per-frame-normalised exponentials u_t = exp(x_t - max x_t) with four lanes per frame, and publishes
+// them through a shared-memory ring.  The FAC consumers gather u_t[y_s] for their own target positions
+// straight from that ring (labels live in registers), so nothing on the producer side scales with S.
 // The recurrences run in the real domain -- no exp/log on the critical path:
 //   FCC: P_t = s_t * u_t o (E P_{t-1}),  E = exp(A - max A) held in REGISTERS (one row per lane, the
 //        rows beyond 32 split four-ways by column), s_t = exact power of two from a single REDUX max.
 //   FAC: bidiagonal; 8 consecutive target positions per lane, block floating point (one power-of-two
 //        exponent per lane), neighbours exchanged with one shuffle; no warp-wide reduction at all.
+// State is written utterance-major ([N,tp,*], see asg_layout_t): every chain writes one sequential stream.
 // See DESIGN.md for the numerics and tests/scaled_model.py for the executable specification.
 #include "asg_common.cuh"
 #include "asg_internal.h"
 
 namespace asg {
 
+constexpr int FB = 8;             // frames per producer batch (4 lanes per frame)
+constexpr int NRAW = 4;           // raw batches in flight (cp.async groups)
+constexpr int RING = NRAW * FB;   // depth of the u ring, in frames
+
+// ---------------------------------------------------------------------------------------------
+// producer: x rows -> u ring.  Shared by the FCC and FAC kernels.
+//   raw   [NRAW][FB][rp]   landing zone of the cp.async copies
+//   uring [RING][up]       u_t = exp(x_t - m_t); entries l >= L of a row are 0
+//   consumed_min()         frames every consumer has finished with
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool BETA, typename ConsumedFn>
+__device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int rp, T *uring, int up, int *produced,
+                                              double *msum_out, int *msum_ready, ConsumedFn consumed_min, int n, int Tn,
+                                              int lane) {
+    const int L = a.d.L;
+    const int f = lane >> 2, sub = lane & 3;
+    const T *xn = a.x + (int64_t)n * a.x_sn;
+    const T ninf = Num<T>::neg_inf();
+    auto issue = [&](int b) {
+        const int k = b * FB + f;
+        if (k < Tn) {
+            const int t = BETA ? (Tn - 1 - k) : k;
+            const T *row = xn + (int64_t)t * a.x_st;
+            T *dst = raw + ((size_t)(b % NRAW) * FB + f) * rp;
+            for (int l = sub; l < L; l += 4) cp_async<sizeof(T)>(dst + l, row + (int64_t)l * a.x_sl);
+        }
+    };
+    const int nb = (Tn + FB - 1) / FB;
+    for (int b = 0; b < NRAW; ++b) {
+        if (b < nb) issue(b);
+        cp_async_commit();
+    }
+    double msum = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait<NRAW - 1>();
+        const int k = b * FB + f;
+        const bool valid = k < Tn;
+        const T *src = raw + ((size_t)(b % NRAW) * FB + f) * rp;
+        T m = ninf;
+        if (valid)
+            for (int l = sub; l < L; l += 4) m = tmax(m, src[l]);
+        m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 1));
+        m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 2));
+        if (!(m > ninf)) m = T(0);                     // an all -inf frame
+        const int hi = min((b + 1) * FB, Tn);
+        if (hi > RING) {                               // the slots of this batch must have been released
+            while (consumed_min() < hi - RING) __nanosleep(32);
+        }
+        T *dst = uring + (size_t)(k % RING) * up;
+        if (valid)                                     // (slots of frames >= Tn belong to frames not yet consumed)
+            for (int l = sub; l < up; l += 4) dst[l] = (l < L) ? Num<T>::exp_(src[l] - m) : T(0);
+        if (valid && sub == 0) msum += (double)m;
+        if (b + NRAW < nb) issue(b + NRAW);            // each lane re-fills only elements it has consumed itself
+        cp_async_commit();
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            st_volatile_s32(produced, hi);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(ASG_FULL_MASK, msum, o);
+    if (lane == 0) {
+        *msum_out = msum;
+        __threadfence_block();
+        st_volatile_s32(msum_ready, 1);
+    }
+}
+
+__device__ __forceinline__ double wait_msum(const double *msum, const int *msum_ready) {
+    while (ld_volatile_s32(msum_ready) == 0) __nanosleep(32);
+    __threadfence_block();
+    return *reinterpret_cast<const volatile double *>(msum);
+}
+
 // =============================================================================================
 // FCC
 // =============================================================================================
-constexpr int FCC_PF = 16;   // cp.async rows in flight
-constexpr int FCC_D = 16;    // depth of the u ring
-
 template <typename T, int LP>
 struct FccSmem {
-    T raw[FCC_PF][LP];
-    T uring[FCC_D][LP];
-    T mxring[FCC_D];
+    alignas(16) T raw[NRAW * FB * LP];
+    alignas(16) T uring[RING * LP];
     alignas(16) T pvec[2][LP];
+    double msum;
+    int msum_ready;
     int produced;
     int consumed;
 };
@@ -59,47 +136,6 @@ __device__ __forceinline__ T transition_max(const T *A, int64_t s0, int64_t s1, 
 }
 
 template <typename T, int LP, bool BETA>
-__device__ void fcc_producer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) {
-    const int L = a.d.L;
-    const T *xn = a.x + (int64_t)n * a.x_sn;
-    auto issue = [&](int k) {
-        const int t = BETA ? (Tn - 1 - k) : k;
-        const T *row = xn + (int64_t)t * a.x_st;
-        if (lane < L) cp_async<sizeof(T)>(&sm.raw[k % FCC_PF][lane], row + (int64_t)lane * a.x_sl);
-        if (LP > 32 && lane + 32 < L) cp_async<sizeof(T)>(&sm.raw[k % FCC_PF][lane + 32], row + (int64_t)(lane + 32) * a.x_sl);
-    };
-    for (int k = 0; k < FCC_PF; ++k) {
-        if (k < Tn) issue(k);
-        cp_async_commit();
-    }
-    for (int k = 0; k < Tn; ++k) {
-        cp_async_wait<FCC_PF - 1>();
-        const T ninf = Num<T>::neg_inf();
-        T v0 = (lane < L) ? sm.raw[k % FCC_PF][lane] : ninf;
-        T v1 = (LP > 32 && lane + 32 < L) ? sm.raw[k % FCC_PF][lane + 32] : ninf;
-        if (k + FCC_PF < Tn) issue(k + FCC_PF);
-        cp_async_commit();
-        T m = Num<T>::warp_max(tmax(v0, v1));
-        if (!(m > ninf)) m = T(0);                     // an all -inf frame
-        T u0 = (lane < L) ? Num<T>::exp_(v0 - m) : T(0);
-        T u1 = (LP > 32 && lane + 32 < L) ? Num<T>::exp_(v1 - m) : T(0);
-        if (k >= FCC_D) {
-            while (ld_volatile_s32(&sm.consumed) < k - FCC_D + 1) __nanosleep(40);
-        }
-        const int slot = k % FCC_D;
-        if (lane < LP) sm.uring[slot][lane] = u0;
-        if (LP > 32 && lane + 32 < LP) sm.uring[slot][lane + 32] = u1;
-        if (lane == 0) sm.mxring[slot] = m;
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            st_volatile_s32(&sm.produced, k + 1);
-        }
-    }
-    cp_async_wait<0>();
-}
-
-template <typename T, int LP, bool BETA>
 __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) {
     constexpr bool FULL = (LP >= 32);
     constexpr int REM = FULL ? LP - 32 : LP;                      // rows handled with a column split
@@ -107,7 +143,9 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
     constexpr int CH = 32 / RP;                                   // column chunks
     constexpr int CL = LP / CH;                                   // columns per chunk
     constexpr int RBASE = FULL ? 32 : 0;
-    const int L = a.d.L, N = a.d.N;
+    const int L = a.d.L;
+    const int lpi = (int)a.ctx.lpi;
+    const int64_t tp = a.ctx.tp;
     const int rr = lane % RP, cc = lane / RP;
     const int row2 = RBASE + rr;
     const bool has2 = (REM > 0) && (rr < REM);
@@ -137,7 +175,6 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
     T *state = BETA ? a.fcc_beta : a.fcc_alpha;
     int ready = 0;
     int esum = 0;
-    double msum = 0.0;
     int cur = 0;
     T v1 = T(0), v2 = T(0);     // this lane's rows of the current state vector
     T last_w1 = T(0), last_w2 = T(0);
@@ -148,10 +185,9 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
             while ((ready = ld_volatile_s32(&sm.produced)) <= k) __nanosleep(20);
             __threadfence_block();
         }
-        const int slot = k % FCC_D;
-        const T u1 = FULL ? sm.uring[slot][lane] : T(0);
-        const T u2 = has2 ? sm.uring[slot][row2] : T(0);
-        msum += (double)sm.mxring[slot];
+        const T *urow = sm.uring + (size_t)(k % RING) * LP;
+        const T u1 = FULL ? urow[lane] : T(0);
+        const T u2 = has2 ? urow[row2] : T(0);
         T sc = T(1);
         if (k == 0) {
             if (BETA) { v1 = (FULL && lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
@@ -187,25 +223,25 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
             esum += e;
         }
         // ---- publish the new state ---------------------------------------------------------------
-        const int64_t base = ((int64_t)t * N + n) * L;
+        const int64_t base = ((int64_t)n * tp + t) * lpi;
         T w1 = v1, w2 = v2;                       // what feeds the next mat-vec
         if (BETA) { w1 = v1 * u1; w2 = v2 * u2; }
         if (FULL) {
             sm.pvec[cur ^ 1][lane] = w1;
-            if (lane < L && state) {
+            if (lane < lpi && state) {
                 st_stream(state + base + lane, v1);
                 if (BETA) st_stream(a.ctx.fcc_w + base + lane, w1);
             }
         }
         if (has2 && cc == 0) {
             sm.pvec[cur ^ 1][row2] = w2;
-            if (row2 < L && state) {
+            if (row2 < lpi && state) {
                 st_stream(state + base + row2, v2);
                 if (BETA) st_stream(a.ctx.fcc_w + base + row2, w2);
             }
         }
         if (!FULL && !has2 && cc == 0 && row2 < LP) sm.pvec[cur ^ 1][row2] = T(0);
-        if (!BETA && lane == 0) a.ctx.fcc_scale[(int64_t)t * N + n] = sc;
+        if (!BETA && lane == 0) a.ctx.fcc_scale[(int64_t)n * tp + t] = sc;
         last_w1 = w1; last_w2 = w2;
         cur ^= 1;
         __syncwarp();
@@ -214,6 +250,7 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
     // ---- score: log(sum of the final weighted state) + bookkeeping -----------------------------
     if (Tn > 0) {
         T tot = warp_sum((FULL ? last_w1 : T(0)) + ((has2 && cc == 0) ? last_w2 : T(0)));
+        const double msum = wait_msum(&sm.msum, &sm.msum_ready);
         if (lane == 0) {
             const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
                                  (double)esum * 0.6931471805599453094;
@@ -230,125 +267,72 @@ template <typename T, int LP>
 __global__ void __launch_bounds__(64) fcc_scan_kernel(const ScanArgs<T> a) {
     __shared__ FccSmem<T, LP> sm;
     const int n = blockIdx.x;
-    const int role = blockIdx.y == 0 ? a.role0 : a.role1;
+    const int dir = blockIdx.y == 0 ? a.dir0 : a.dir1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { sm.produced = 0; sm.consumed = 0; }
+    if (threadIdx.x == 0) { sm.produced = 0; sm.consumed = 0; sm.msum_ready = 0; }
     __syncthreads();
     int Tn = a.il ? (int)a.il[n] : a.d.T;
     Tn = max(0, min(Tn, a.d.T));
-    if (role == 0) {
+    auto cons = [&]() { return ld_volatile_s32(&sm.consumed); };
+    if (dir == 0) {
         if (warp == 0) fcc_consumer<T, LP, false>(a, sm, n, Tn, lane);
-        else fcc_producer<T, LP, false>(a, sm, n, Tn, lane);
+        else scan_producer<T, false>(a, sm.raw, LP, sm.uring, LP, &sm.produced, &sm.msum, &sm.msum_ready, cons, n, Tn, lane);
     } else {
         if (warp == 0) fcc_consumer<T, LP, true>(a, sm, n, Tn, lane);
-        else fcc_producer<T, LP, true>(a, sm, n, Tn, lane);
+        else scan_producer<T, true>(a, sm.raw, LP, sm.uring, LP, &sm.produced, &sm.msum, &sm.msum_ready, cons, n, Tn, lane);
     }
 }
 
 // =============================================================================================
 // FAC
 // =============================================================================================
-constexpr int FAC_PF = 8;    // cp.async rows in flight
-
 template <typename T> struct FacSmemView {
-    T *raw;        // [FAC_PF][L]
-    T *urow;       // [L]
-    T *gring;      // [D][sp]
-    T *mxring;     // [D]
+    T *raw;        // [NRAW*FB][lpi]
+    T *uring;      // [RING][up]      up = lpi + 4: entries [lpi, up) are the always-zero slots
     T *xval;       // [2][W+1]  boundary mantissas between consumer warps
     int *xexp;     // [2][W+1]
     int *ylab;     // [sp]
     T *red;        // [W]
-    int *produced; // [1]
+    double *msum;  // [1]
+    int *flags;    // [0] produced, [1] msum_ready
     int *consumed; // [W]
 };
 
 template <typename T>
-__host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, int L, int sp, int W, int D) {
+__host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, int lpi, int sp, int W) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
-    size_t o_raw = take(sizeof(T) * FAC_PF * L);
-    size_t o_urow = take(sizeof(T) * L);
-    size_t o_gring = take(sizeof(T) * (size_t)D * sp);
-    size_t o_mx = take(sizeof(T) * D);
+    const int up = lpi + 4;
+    size_t o_raw = take(sizeof(T) * NRAW * FB * lpi);
+    size_t o_uring = take(sizeof(T) * RING * up);
     size_t o_xval = take(sizeof(T) * 2 * (W + 1));
     size_t o_xexp = take(sizeof(int) * 2 * (W + 1));
     size_t o_ylab = take(sizeof(int) * sp);
     size_t o_red = take(sizeof(T) * W);
-    size_t o_prod = take(sizeof(int) * 4);
+    size_t o_msum = take(sizeof(double));
+    size_t o_flags = take(sizeof(int) * 4);
     size_t o_cons = take(sizeof(int) * W);
     if (v) {
-        v->raw = (T *)(base + o_raw); v->urow = (T *)(base + o_urow); v->gring = (T *)(base + o_gring);
-        v->mxring = (T *)(base + o_mx); v->xval = (T *)(base + o_xval); v->xexp = (int *)(base + o_xexp);
-        v->ylab = (int *)(base + o_ylab); v->red = (T *)(base + o_red); v->produced = (int *)(base + o_prod);
-        v->consumed = (int *)(base + o_cons);
+        v->raw = (T *)(base + o_raw); v->uring = (T *)(base + o_uring);
+        v->xval = (T *)(base + o_xval); v->xexp = (int *)(base + o_xexp);
+        v->ylab = (int *)(base + o_ylab); v->red = (T *)(base + o_red); v->msum = (double *)(base + o_msum);
+        v->flags = (int *)(base + o_flags); v->consumed = (int *)(base + o_cons);
     }
     return off;
 }
 
-template <typename T, int W, bool BETA>
-__device__ void fac_producer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, int Tn, int Sn, int D, int lane) {
-    const int L = a.d.L;
-    const int sp = (int)a.ctx.sp;
-    const T *xn = a.x + (int64_t)n * a.x_sn;
-    auto issue = [&](int k) {
-        const int t = BETA ? (Tn - 1 - k) : k;
-        const T *row = xn + (int64_t)t * a.x_st;
-        T *dst = sm.raw + (size_t)(k % FAC_PF) * L;
-        for (int i = lane; i < L; i += 32) cp_async<sizeof(T)>(dst + i, row + (int64_t)i * a.x_sl);
-    };
-    for (int k = 0; k < FAC_PF; ++k) {
-        if (k < Tn) issue(k);
-        cp_async_commit();
-    }
-    const T ninf = Num<T>::neg_inf();
-    for (int k = 0; k < Tn; ++k) {
-        cp_async_wait<FAC_PF - 1>();
-        const T *src = sm.raw + (size_t)(k % FAC_PF) * L;
-        T m = ninf;
-        for (int i = lane; i < L; i += 32) m = tmax(m, src[i]);
-        m = Num<T>::warp_max(m);
-        if (!(m > ninf)) m = T(0);
-        for (int i = lane; i < L; i += 32) sm.urow[i] = Num<T>::exp_(src[i] - m);
-        if (k + FAC_PF < Tn) issue(k + FAC_PF);   // this lane's own elements of the slot are consumed
-        cp_async_commit();
-        __syncwarp();
-        if (k >= D) {
-            const int need = k - D + 1;
-            for (;;) {
-                int c = (lane < W) ? ld_volatile_s32(&sm.consumed[lane]) : 0x7fffffff;
-                c = __reduce_min_sync(ASG_FULL_MASK, c);
-                if (c >= need) break;
-                __nanosleep(40);
-            }
-        }
-        T *g = sm.gring + (size_t)(k % D) * sp;
-        for (int s = lane; s < sp; s += 32) {
-            const int lab = sm.ylab[s];
-            g[s] = (lab >= 0) ? sm.urow[lab] : T(0);
-        }
-        if (lane == 0) sm.mxring[k % D] = m;
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            st_volatile_s32(sm.produced, k + 1);
-        }
-    }
-    cp_async_wait<0>();
-}
-
-template <typename T, int W>
-__device__ __forceinline__ void fac_consumer_sync() {
+__device__ __forceinline__ void fac_consumer_sync(int W) {
     if (W == 1) __syncwarp();
     else named_bar_sync(1, 32 * W);
 }
 
-template <typename T, int W, bool BETA>
-__device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, int Tn, int Sn, int D, T Rb,
-                             const T (&h)[ASG_BLK], const T (&dd)[ASG_BLK], int warp, int lane) {
+template <typename T, bool BETA>
+__device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, int n, int Tn, int Sn, T Rb,
+                             const T (&h)[ASG_BLK], const T (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
     // dd[j]: alpha -> edge (s-1 -> s) into own state j;  beta -> edge (s -> s+1) out of own state j
-    const int N = a.d.N;
-    const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk;
+    const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp;
+    const int up = (int)a.ctx.lpi + 4;
+    const int64_t tp = a.ctx.tp;
     const int gl = warp * 32 + lane;            // global lane = block index
     const int s0 = gl * ASG_BLK;
     const bool owns = s0 < sp;
@@ -360,20 +344,18 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, in
     int Eme = 0;
     T mymax = T(0);      // max of what feeds the next step (alpha: v, beta: w)
     int ready = 0;
-    double msum = 0.0;
     int cur = 0;
 
     for (int k = 0; k < Tn; ++k) {
         const int t = BETA ? (Tn - 1 - k) : k;
         if (k >= ready) {
-            while ((ready = ld_volatile_s32(sm.produced)) <= k) __nanosleep(20);
+            while ((ready = ld_volatile_s32(&sm.flags[0])) <= k) __nanosleep(20);
             __threadfence_block();
         }
-        const T *g = sm.gring + (size_t)(k % D) * sp;
+        const T *urow = sm.uring + (size_t)(k % RING) * up;
         T ub[ASG_BLK];
 #pragma unroll
-        for (int j = 0; j < ASG_BLK; ++j) ub[j] = owns ? g[s0 + j] : T(0);
-        msum += (double)sm.mxring[k % D];
+        for (int j = 0; j < ASG_BLK; ++j) ub[j] = urow[lab[j]];
 
         if (k == 0) {
 #pragma unroll
@@ -440,20 +422,20 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, in
 
         // store mantissas + exponent
         if (owns && state) {
-            T *dst = state + ((int64_t)t * N + n) * sp + s0;
-#pragma unroll
-            for (int j = 0; j < ASG_BLK; ++j) st_stream(dst + j, v[j]);
-            if (gl < nblk) estate[((int64_t)t * N + n) * nblk + gl] = Eme;
+            const int64_t row = (int64_t)n * tp + t;
+            store8_stream(state + row * sp + s0, v);
+            if (gl < nblk) estate[row * nbp + gl] = Eme;
         }
         if (W > 1) {
             if (!BETA && lane == 31) { sm.xval[(cur ^ 1) * (W + 1) + warp] = v[ASG_BLK - 1]; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
             if (BETA && lane == 0) { sm.xval[(cur ^ 1) * (W + 1) + warp] = w[0]; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
         }
         cur ^= 1;
-        fac_consumer_sync<T, W>();
+        fac_consumer_sync(W);
         if (lane == 0) st_volatile_s32(&sm.consumed[warp], k + 1);
     }
     // ---- score ------------------------------------------------------------------------------------
+    const double msum = (Tn > 0) ? wait_msum(sm.msum, &sm.flags[1]) : 0.0;
     if (gl == 0) {
         double score = 0.0;
         if (Tn > 0) {
@@ -479,15 +461,15 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int n, in
     }
 }
 
-template <typename T, int W>
-__global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T> a, int D) {
+template <typename T>
+__global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int W) {
     extern __shared__ __align__(16) char smem_raw[];
     FacSmemView<T> sm;
     const int L = a.d.L, S = a.d.S;
-    const int sp = (int)a.ctx.sp;
-    fac_smem_carve<T>(&sm, smem_raw, L, sp, W, D);
+    const int sp = (int)a.ctx.sp, lpi = (int)a.ctx.lpi, up = lpi + 4;
+    fac_smem_carve<T>(&sm, smem_raw, lpi, sp, W);
     const int n = blockIdx.x;
-    const int role = blockIdx.y == 0 ? a.role0 : a.role1;
+    const int dir = blockIdx.y == 0 ? a.dir0 : a.dir1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nthreads = 32 * W + 32;
 
@@ -496,7 +478,7 @@ __global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T>
     int Sn = a.tl ? (int)a.tl[n] : S;
     Sn = max(1, min(Sn, S));
 
-    if (threadIdx.x == 0) sm.produced[0] = 0;
+    if (threadIdx.x == 0) { sm.flags[0] = 0; sm.flags[1] = 0; }
     if (threadIdx.x < W) sm.consumed[threadIdx.x] = 0;
     const int64_t *yn = a.y + (int64_t)n * a.y_s0;
     for (int s = threadIdx.x; s < sp; s += nthreads) {
@@ -512,14 +494,16 @@ __global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T>
     const int s0 = gl * ASG_BLK;
     const T ninf = Num<T>::neg_inf();
     T Hs[ASG_BLK], Ds[ASG_BLK];   // log-domain; Ds: edge s -> s+1
+    int lab[ASG_BLK];             // label of each own position (lpi = the always-zero slot of a u row)
     T lmax = ninf;
     if (consumer) {
 #pragma unroll
         for (int j = 0; j < ASG_BLK; ++j) {
             const int s = s0 + j;
-            Hs[j] = ninf; Ds[j] = ninf;
+            Hs[j] = ninf; Ds[j] = ninf; lab[j] = lpi;
             if (s < Sn) {
                 const int c = sm.ylab[s];
+                lab[j] = c;
                 Hs[j] = a.A[c * a.A_s0 + c * a.A_s1];
                 if (s + 1 < Sn) { const int nx = sm.ylab[s + 1]; Ds[j] = a.A[nx * a.A_s0 + c * a.A_s1]; }
                 if (Hs[j] < -ninf) lmax = tmax(lmax, Hs[j]);
@@ -535,8 +519,13 @@ __global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T>
     if (!(Rb > ninf)) Rb = T(0);
 
     if (!consumer) {
-        if (role == 0) fac_producer<T, W, false>(a, sm, n, Tn, Sn, D, lane);
-        else fac_producer<T, W, true>(a, sm, n, Tn, Sn, D, lane);
+        auto cons = [&]() {
+            int c = 0x7fffffff;
+            for (int q = 0; q < W; ++q) c = min(c, ld_volatile_s32(&sm.consumed[q]));
+            return c;
+        };
+        if (dir == 0) scan_producer<T, false>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, n, Tn, lane);
+        else scan_producer<T, true>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, n, Tn, lane);
         return;
     }
     T h[ASG_BLK], dout[ASG_BLK];
@@ -545,7 +534,7 @@ __global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T>
         h[j] = (Hs[j] == ninf) ? T(0) : Num<T>::exp_(Hs[j] - Rb);
         dout[j] = (Ds[j] == ninf) ? T(0) : Num<T>::exp_(Ds[j] - Rb);
     }
-    if (role == 0) {
+    if (dir == 0) {
         // publish h, d for the gradient assembly, and the lengths
         if (s0 < sp) {
 #pragma unroll
@@ -569,9 +558,9 @@ __global__ void __launch_bounds__(32 * W + 32) fac_scan_kernel(const ScanArgs<T>
         }
 #pragma unroll
         for (int j = 0; j < ASG_BLK; ++j) din[j] = (j == 0) ? left : dout[(j + ASG_BLK - 1) % ASG_BLK];
-        fac_consumer<T, W, false>(a, sm, n, Tn, Sn, D, Rb, h, din, warp, lane);
+        fac_consumer<T, false>(a, sm, W, n, Tn, Sn, Rb, h, din, lab, warp, lane);
     } else {
-        fac_consumer<T, W, true>(a, sm, n, Tn, Sn, D, Rb, h, dout, warp, lane);
+        fac_consumer<T, true>(a, sm, W, n, Tn, Sn, Rb, h, dout, lab, warp, lane);
     }
 }
 
@@ -592,8 +581,8 @@ static cudaEvent_t pooled_event(int device, int which) {
 }
 
 template <typename T, int LP>
-static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
-    dim3 grid(a.d.N, nroles);
+static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int ndirs, cudaStream_t st) {
+    dim3 grid(a.d.N, ndirs);
     {
         LaunchScope ls(K_FCC_SCAN, st);
         fcc_scan_kernel<T, LP><<<grid, 64, 0, st>>>(a);
@@ -601,44 +590,34 @@ static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int nroles, cudaStream_t 
     return cudaGetLastError();
 }
 
-template <typename T> static cudaError_t launch_fcc(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
+template <typename T> static cudaError_t launch_fcc(const ScanArgs<T> &a, int ndirs, cudaStream_t st) {
     const int L = a.d.L;
-    if (L <= 8) return launch_fcc_lp<T, 8>(a, nroles, st);
-    if (L <= 16) return launch_fcc_lp<T, 16>(a, nroles, st);
-    if (L <= 24) return launch_fcc_lp<T, 24>(a, nroles, st);
-    if (L <= 32) return launch_fcc_lp<T, 32>(a, nroles, st);
-    if (L <= 40) return launch_fcc_lp<T, 40>(a, nroles, st);
-    if (L <= 48) return launch_fcc_lp<T, 48>(a, nroles, st);
-    if (L <= 56) return launch_fcc_lp<T, 56>(a, nroles, st);
-    if (L <= 64) return launch_fcc_lp<T, 64>(a, nroles, st);
+    if (L <= 8) return launch_fcc_lp<T, 8>(a, ndirs, st);
+    if (L <= 16) return launch_fcc_lp<T, 16>(a, ndirs, st);
+    if (L <= 24) return launch_fcc_lp<T, 24>(a, ndirs, st);
+    if (L <= 32) return launch_fcc_lp<T, 32>(a, ndirs, st);
+    if (L <= 40) return launch_fcc_lp<T, 40>(a, ndirs, st);
+    if (L <= 48) return launch_fcc_lp<T, 48>(a, ndirs, st);
+    if (L <= 56) return launch_fcc_lp<T, 56>(a, ndirs, st);
+    if (L <= 64) return launch_fcc_lp<T, 64>(a, ndirs, st);
     return cudaErrorInvalidValue;
 }
 
-template <typename T, int W>
-static cudaError_t launch_fac_w(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
-    const int L = a.d.L, sp = (int)a.ctx.sp;
-    int D = 16;
-    size_t bytes = fac_smem_carve<T>(nullptr, nullptr, L, sp, W, D);
-    while (bytes > 200 * 1024 && D > 2) { D >>= 1; bytes = fac_smem_carve<T>(nullptr, nullptr, L, sp, W, D); }
+template <typename T> static cudaError_t launch_fac(const ScanArgs<T> &a, int ndirs, cudaStream_t st) {
+    const int lanes = (int)a.ctx.nblk;
+    int W = 1;
+    while (W * 32 < lanes) W <<= 1;
+    if (W > 16) return cudaErrorInvalidValue;
+    const size_t bytes = fac_smem_carve<T>(nullptr, nullptr, (int)a.ctx.lpi, (int)a.ctx.sp, W);
     if (bytes > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(fac_scan_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(fac_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    dim3 grid(a.d.N, nroles);
+    dim3 grid(a.d.N, ndirs);
     {
         LaunchScope ls(K_FAC_SCAN, st);
-        fac_scan_kernel<T, W><<<grid, 32 * W + 32, bytes, st>>>(a, D);
+        fac_scan_kernel<T><<<grid, 32 * W + 32, bytes, st>>>(a, W);
     }
     return cudaGetLastError();
-}
-
-template <typename T> static cudaError_t launch_fac(const ScanArgs<T> &a, int nroles, cudaStream_t st) {
-    const int lanes = (int)a.ctx.nblk;
-    if (lanes <= 32) return launch_fac_w<T, 1>(a, nroles, st);
-    if (lanes <= 64) return launch_fac_w<T, 2>(a, nroles, st);
-    if (lanes <= 128) return launch_fac_w<T, 4>(a, nroles, st);
-    if (lanes <= 256) return launch_fac_w<T, 8>(a, nroles, st);
-    if (lanes <= 512) return launch_fac_w<T, 16>(a, nroles, st);
-    return cudaErrorInvalidValue;
 }
 
 template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaStream_t stream) {
@@ -658,14 +637,14 @@ template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaSt
     }
     if (any_fcc) {
         ScanArgs<T> a = a_in;
-        a.role0 = fcc_a ? 0 : 1;
-        a.role1 = 1;
+        a.dir0 = fcc_a ? 0 : 1;
+        a.dir1 = 1;
         if ((e = launch_fcc<T>(a, (fcc_a && fcc_b) ? 2 : 1, stream)) != cudaSuccess) return (int)e;
     }
     if (any_fac) {
         ScanArgs<T> a = a_in;
-        a.role0 = fac_a ? 0 : 1;
-        a.role1 = 1;
+        a.dir0 = fac_a ? 0 : 1;
+        a.dir1 = 1;
         cudaStream_t st = side ? side : stream;
         if ((e = launch_fac<T>(a, (fac_a && fac_b) ? 2 : 1, st)) != cudaSuccess) return (int)e;
         if (side) {

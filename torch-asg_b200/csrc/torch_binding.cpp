@@ -6,8 +6,8 @@
 // What the returned "alpha / beta / gamma / path_contrib" tensors hold differs from the reference by design
 // (asg.py only looks at alpha.shape / full_gamma.shape -- asg.py:28,50,88 -- and hands everything else
 // straight back to our own backward):
-//   alpha / full_gamma         scaled real-domain FCC alpha  [T,N,L]
-//   aligned alpha / gamma      block-floating-point FAC alpha, a [T,N,S] view of a [T,N,sp] buffer
+//   alpha / full_gamma         scaled real-domain FCC alpha: a [T,N,L] view of an utterance-major [N,tp,lpi] buffer
+//   aligned alpha / gamma      block-floating-point FAC alpha: a [T,N,S] view of an utterance-major [N,tp,sp] buffer
 //   beta                       the matching beta state
 //   path_contrib               an opaque uint8 context blob (asg_layout_t) -- NOT a [T-1,N,L,L] tensor
 // There is no CPU path: CPU tensors raise.
@@ -53,6 +53,12 @@ Tensor bytes_like(const Tensor &like, size_t nbytes) {
     return at::empty({(int64_t)nbytes}, like.options().dtype(at::kByte).requires_grad(false));
 }
 
+// [T,N,W] view (what asg.py inspects the shape of) of an utterance-major [N,tp,pitch] state buffer
+Tensor state_view(const Tensor &buf, int64_t T, int64_t W) { return buf.narrow(1, 0, T).narrow(2, 0, W).permute({1, 0, 2}); }
+bool is_state_view(const Tensor &v, int64_t tp, int64_t pitch) {
+    return v.dim() == 3 && v.stride(2) == 1 && v.stride(0) == pitch && v.stride(1) == tp * pitch && v.storage_offset() == 0;
+}
+
 void check_inputs(const Tensor &inputs, const Tensor &transition, int64_t T, int64_t N, int64_t L) {
     check_cuda(inputs, "inputs");
     check_cuda(transition, "transition");
@@ -75,13 +81,13 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> fully_connected_forward(Tensor &input
     Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
     const asg_layout_t lay = layout_of(dt, T, N, L, 1);
     auto opt = inputs.options().requires_grad(false);
-    Tensor alpha = at::empty({T, N, L}, opt), beta = at::empty({T, N, L}, opt), scores = at::empty({N}, opt);
+    Tensor alpha = at::empty({N, lay.tp, lay.lpi}, opt), beta = at::empty({N, lay.tp, lay.lpi}, opt), scores = at::empty({N}, opt);
     Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
     check_rc(asg_scan(dt, ASG_ROLE_FCC_ALPHA | ASG_ROLE_FCC_BETA, inputs.data_ptr(), inputs.stride(0), inputs.stride(1),
                       inputs.stride(2), transition.data_ptr(), transition.stride(0), transition.stride(1), nullptr, 0, 0,
                       il.data_ptr<int64_t>(), nullptr, T, N, L, 1, alpha.data_ptr(), beta.data_ptr(), nullptr, nullptr,
                       ctx.data_ptr(), scores.data_ptr(), nullptr, current_stream()));
-    return {scores, alpha, beta, ctx};
+    return {scores, state_view(alpha, T, L), state_view(beta, T, L), ctx};
 }
 
 // reference: fully_connected_backward, fully_connected_lattice.h:51-60 / .cpp:94-104
@@ -93,6 +99,8 @@ std::tuple<Tensor, Tensor> fully_connected_backward(Tensor &grad_out, Tensor &al
     const asg_layout_t lay = layout_of(dt, T, N, L, 1);
     TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
                 "path_contrib is not a context blob produced by this extension's fully_connected_forward");
+    TORCH_CHECK(is_state_view(alpha, lay.tp, lay.lpi) && is_state_view(beta, lay.tp, lay.lpi),
+                "alpha/beta are not the state tensors produced by this extension's fully_connected_forward");
     Tensor g = grad_out.to(alpha.options());
     auto opt = alpha.options().requires_grad(false);
     Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
@@ -116,14 +124,14 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> force_aligned_forward(Tensor &inputs,
     TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
-    Tensor alpha = at::empty({T, N, lay.sp}, opt), beta = at::empty({T, N, lay.sp}, opt), scores = at::empty({N}, opt);
+    Tensor alpha = at::empty({N, lay.tp, lay.sp}, opt), beta = at::empty({N, lay.tp, lay.sp}, opt), scores = at::empty({N}, opt);
     Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
     check_rc(asg_scan(dt, ASG_ROLE_FAC_ALPHA | ASG_ROLE_FAC_BETA, inputs.data_ptr(), inputs.stride(0), inputs.stride(1),
                       inputs.stride(2), transition.data_ptr(), transition.stride(0), transition.stride(1),
                       y.data_ptr<int64_t>(), y.stride(0), y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L,
                       S, nullptr, nullptr, alpha.data_ptr(), beta.data_ptr(), ctx.data_ptr(), nullptr, scores.data_ptr(),
                       current_stream()));
-    return {scores, alpha.narrow(2, 0, S), beta.narrow(2, 0, S), ctx};
+    return {scores, state_view(alpha, T, S), state_view(beta, T, S), ctx};
 }
 
 // reference: force_aligned_backward, force_aligned_lattice.h:56-69 / .cpp:321-356
@@ -136,7 +144,7 @@ std::tuple<Tensor, Tensor> force_aligned_backward(Tensor &grad_out, Tensor &alph
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
                 "path_contrib is not a context blob produced by this extension's force_aligned_forward");
-    TORCH_CHECK(alpha.stride(1) == lay.sp && beta.stride(1) == lay.sp && alpha.stride(2) == 1,
+    TORCH_CHECK(is_state_view(alpha, lay.tp, lay.sp) && is_state_view(beta, lay.tp, lay.sp),
                 "alpha/beta are not the state tensors produced by this extension's force_aligned_forward");
     Tensor y = as_device_long(targets, alpha, "targets");
     Tensor g = grad_out.to(alpha.options());
@@ -186,8 +194,8 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fast_asg_gpu_forward(
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
     Tensor full = at::empty({N}, opt), aligned = at::empty({N}, opt);
-    Tensor fcc_alpha = at::empty({T, N, L}, opt);
-    Tensor fac_alpha = at::empty({T, N, lay.sp}, opt);
+    Tensor fcc_alpha = at::empty({N, lay.tp, lay.lpi}, opt);
+    Tensor fac_alpha = at::empty({N, lay.tp, lay.sp}, opt);
     // the two beta states travel in one opaque tensor (the "aligned_path_contrib" slot)
     const size_t fb = (lay.fcc_state_bytes + 255) / 256 * 256;
     Tensor betas = bytes_like(inputs, fb + lay.fac_state_bytes);
@@ -197,7 +205,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fast_asg_gpu_forward(
                       transition.data_ptr(), transition.stride(0), transition.stride(1), y.data_ptr<int64_t>(), y.stride(0),
                       y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, fcc_alpha.data_ptr(), bp,
                       fac_alpha.data_ptr(), bp + fb, ctx.data_ptr(), full.data_ptr(), aligned.data_ptr(), current_stream()));
-    return {full, aligned, fcc_alpha, fac_alpha.narrow(2, 0, S), ctx, betas};
+    return {full, aligned, state_view(fcc_alpha, T, L), state_view(fac_alpha, T, S), ctx, betas};
 }
 
 // reference: fast_asg_gpu_backward, streamlined_fast_gpu.h:50-68 / .cpp:236-297
@@ -212,7 +220,7 @@ std::tuple<Tensor, Tensor> fast_asg_gpu_backward(Tensor &grad_full, Tensor &grad
     const size_t fb = (lay.fcc_state_bytes + 255) / 256 * 256;
     TORCH_CHECK((size_t)full_path_contrib.numel() == lay.ctx_bytes && full_path_contrib.scalar_type() == at::kByte &&
                     (size_t)aligned_path_contrib.numel() == fb + lay.fac_state_bytes &&
-                    aligned_gamma.stride(1) == lay.sp && full_gamma.is_contiguous(),
+                    is_state_view(aligned_gamma, lay.tp, lay.sp) && is_state_view(full_gamma, lay.tp, lay.lpi),
                 "saved tensors were not produced by this extension's fast_asg_gpu_forward");
     Tensor y = as_device_long(targets, full_gamma, "targets");
     Tensor gf = grad_full.to(full_gamma.options()), ga = grad_aligned.to(full_gamma.options());
