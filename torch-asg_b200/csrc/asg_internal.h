@@ -72,6 +72,7 @@ template <typename T> struct GradArgs {
     T *grad_x, *grad_A;
     T *partials;                // [grid, L*L] per-CTA partial transition gradients
     int tb;                     // frames per tile
+    int nstage;                 // depth of the shared-memory tile ring
     int tiles_t;                // ceil(T / tb)
     int num_tiles;              // tiles_t * N
 };
