@@ -19,6 +19,8 @@ template <> struct Num<float> {
     __device__ __forceinline__ static float exp_(float v) { return expf(v); }
     __device__ __forceinline__ static float log_(float v) { return logf(v); }
     __device__ __forceinline__ static float neg_inf() { return __int_as_float(0xff800000); }
+    __device__ __forceinline__ static float tiny() { return 1.0e-37f; }
+    __device__ __forceinline__ static float prod_scale() { return 1.329227995784916e36f; }      // 2^120
     // 2^k for k in [-126,127] (clamped)
     __device__ __forceinline__ static float exp2i(int k) {
         k = max(-126, min(127, k));
@@ -51,6 +53,8 @@ template <> struct Num<double> {
     __device__ __forceinline__ static double exp_(double v) { return exp(v); }
     __device__ __forceinline__ static double log_(double v) { return log(v); }
     __device__ __forceinline__ static double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+    __device__ __forceinline__ static double tiny() { return 1.0e-300; }
+    __device__ __forceinline__ static double prod_scale() { return 9.745314011399999e288; }     // 2^960
     __device__ __forceinline__ static double exp2i(int k) {
         k = max(-1022, min(1023, k));
         return __hiloint2double((k + 1023) << 20, 0);

@@ -10,15 +10,20 @@
 // What it streams (per frame t, utterance n): the scaled FCC states alpha[L], beta[L], u*beta[L], the FAC
 // block-floating-point states alpha[sp], beta[sp] with their block exponents, and writes grad_x[L] exactly
 // once.  Nothing like the reference's path_contrib[T-1,N,L,L] exists: the edge posteriors are rebuilt from
-// alpha[t-1] and u*beta[t] on the fly and contracted into a per-CTA L x L register tile
-// (G += w_t (x) alpha_{t-1}); the FAC label scatter is a per-utterance CSR gather in shared memory instead of
-// T*N*S global atomics; every reduction has a fixed order, so results are run-to-run deterministic.
+// alpha[t-1] and u*beta[t] on the fly.
 //
-// Structure: tile = (utterance n, TB consecutive frames).  State is utterance-major, so a tile of every state
-// array is ONE contiguous chunk: a producer warp fetches it with ~7 bulk (TMA) copies (cp.async.bulk ->
-// UBLKCP) into a two-stage shared-memory ring guarded by mbarriers, while eight consumer warps work on the
-// previous tile.  Tiles are dealt in n-major order to a persistent grid so a CTA mostly stays on one utterance
-// (its CSR / transition rows stay in shared memory).
+// Structure.  tile = (utterance n, TB consecutive frames).  State is utterance-major, so a tile of every state
+// array is ONE contiguous chunk: a producer warp fetches it with 8 bulk (TMA) copies (cp.async.bulk -> UBLKCP)
+// into an NS-stage shared-memory ring guarded by mbarriers.  Each of the NW consumer warps then owns whole
+// frames of the tile -- one warp per (utterance, frame) slice, lane = one 8-position block of the target /
+// one or two labels -- and does everything for its frame in registers with no block-wide barrier:
+//   FAC posterior (block-floating-point alignment, one REDUX + one shuffle tree), label scatter into the
+//   warp's private fixed-point bins (integer shared-memory atomics: order-independent, so deterministic),
+//   edge posteriors into per-lane register accumulators, FCC posterior, the FCC transition-gradient outer
+//   product into a per-lane register slice of G, and the one coalesced store of the grad_x row.
+// Warps only meet at utterance boundaries (to flush the per-position edge sums through a label CSR into the
+// CTA's L x L matrix, fixed order) and at the end.  Every reduction has a fixed order or is integer:
+// results are run-to-run deterministic.
 #include <climits>
 #include <cstdlib>
 #include "asg_common.cuh"
@@ -26,19 +31,49 @@
 
 namespace asg {
 
-constexpr int GRAD_CWARPS = 8;                        // consumer warps
-constexpr int GRAD_CONSUMERS = GRAD_CWARPS * 32;
-constexpr int GRAD_THREADS = GRAD_CONSUMERS + 32;     // + one producer warp
+constexpr int GRAD_MAX_CWARPS = 8;     // consumer warps (+ one producer warp)
+constexpr int GRAD_LBINS = 72;         // label bins per warp: L <= 64, bin L = trash (padding positions)
+
+// Fixed-point images (integers add in any order with the same result, so shared-memory atomics stay deterministic):
+//   posterior p of one position in one frame, 0 <= p <= 1, a frame sums to 1  -> p * kPost  (int32 / int64 bins)
+//   edge sums: posteriors (already in kPost units) summed over <= 2^24 frames -> 64-bit, kEdge units per unit mass
+template <typename T> struct Fix;
+template <> struct Fix<float> {
+    typedef int bin_t;
+    static constexpr float kPost = 1073741824.0f;                 // 2^30
+    static constexpr float kInvPost = 1.0f / 1073741824.0f;
+    __device__ __forceinline__ static int to_fix(float q) { return __float2int_rn(q); }
+    __device__ __forceinline__ static float from_fix(int q) { return (float)q; }
+    __device__ __forceinline__ static void add(int *bin, int q) { atomicAdd(bin, q); }
+    // accumulators hold kPost * mass (mass <= 2^24): 2^32 units per unit mass
+    __device__ __forceinline__ static unsigned long long edge_fix(float acc) { return (unsigned long long)__float2ll_rn(acc * 4.0f); }
+    __device__ __forceinline__ static float edge_unfix(unsigned long long q) { return (float)((double)(long long)q * (1.0 / 4294967296.0)); }
+};
+template <> struct Fix<double> {
+    typedef unsigned long long bin_t;
+    static constexpr double kPost = 4611686018427387904.0;       // 2^62
+    static constexpr double kInvPost = 1.0 / 4611686018427387904.0;
+    __device__ __forceinline__ static unsigned long long to_fix(double q) { return (unsigned long long)__double2ll_rn(q); }
+    __device__ __forceinline__ static double from_fix(unsigned long long q) { return (double)(long long)q; }
+    __device__ __forceinline__ static void add(unsigned long long *bin, unsigned long long q) { atomicAdd(bin, q); }
+    // 2^38 units per unit mass
+    __device__ __forceinline__ static unsigned long long edge_fix(double acc) { return (unsigned long long)__double2ll_rn(acc * (1.0 / 16777216.0)); }
+    __device__ __forceinline__ static double edge_unfix(unsigned long long q) { return (double)(long long)q * (1.0 / 274877906944.0); }
+};
+
+// approximate (float) / exact (double) quotient for the edge posteriors
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 
 // shared-memory map: [per-CTA block][stage 0][stage 1]...
 struct GradMap {
     // per stage, byte offsets from the stage base
-    size_t oA, oB, oEa, oEb, oBnd, oZb, oFa, oFb, oFw, stage_bytes;
+    size_t oA, oB, oEa, oEb, oFa, oFb, oFw, oSc, stage_bytes;
     // per CTA, byte offsets from the base
-    size_t o_hh, o_din, o_tH, o_tD, o_ylab, o_order, o_lstart, o_Gal, o_bars, o_stages, total;
+    size_t o_hh, o_din, o_ylab, o_Gal, o_Gf, o_galfix, o_bins, o_acc, o_bars, o_stages, total;
 };
 
-__host__ __device__ inline GradMap grad_map(size_t eb, int L, int lpi, int sp, int nbp, int TB, int nstage, bool fcc, bool fac) {
+__host__ __device__ inline GradMap grad_map(size_t eb, int L, int lpi, int sp, int nbp, int TB, int nstage, int nw, bool fcc, bool fac) {
     GradMap m;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
@@ -46,28 +81,27 @@ __host__ __device__ inline GradMap grad_map(size_t eb, int L, int lpi, int sp, i
     m.oB = take(fac ? eb * (size_t)TB * sp : 0);
     m.oEa = take(fac ? sizeof(int) * (size_t)(TB + 1) * nbp : 0);
     m.oEb = take(fac ? sizeof(int) * (size_t)TB * nbp : 0);
-    m.oBnd = take(fac ? eb * (size_t)(TB + 1) * nbp : 0);
-    m.oZb = take(fac ? eb * (size_t)TB : 0);
     m.oFa = take(fcc ? eb * (size_t)(TB + 1) * lpi : 0);
     m.oFb = take(fcc ? eb * (size_t)TB * lpi : 0);
     m.oFw = take(fcc ? eb * (size_t)TB * lpi : 0);
+    m.oSc = take(fcc ? eb * (size_t)((TB + 3) / 4 * 4) : 0);
     m.stage_bytes = align_up(off, 128);
     off = 0;
     m.o_hh = take(fac ? eb * sp : 0);
     m.o_din = take(fac ? eb * sp : 0);
-    m.o_tH = take(fac ? eb * sp : 0);
-    m.o_tD = take(fac ? eb * sp : 0);
     m.o_ylab = take(fac ? sizeof(int) * sp : 0);
-    m.o_order = take(fac ? sizeof(int) * sp : 0);
-    m.o_lstart = take(fac ? sizeof(int) * (L + 1) : 0);
-    m.o_Gal = take(fac ? eb * (size_t)L * L : 0);
-    m.o_bars = take(sizeof(uint64_t) * 2 * 4);
+    m.o_Gal = take(eb * (size_t)L * L);
+    m.o_Gf = take(fcc ? eb * (size_t)L * L : 0);
+    m.o_galfix = take(fac ? 8 * 2 * (size_t)L * L : 0);
+    m.o_bins = take(fac ? 8 * (size_t)nw * GRAD_LBINS : 0);
+    m.o_acc = take((fac && sp > 256) ? eb * (size_t)nw * 2 * sp : 0);
+    m.o_bars = take(sizeof(uint64_t) * 2 * 8);
     m.o_stages = align_up(off, 128);
     m.total = m.o_stages + m.stage_bytes * nstage;
     return m;
 }
 
-// 8 consecutive elements (32-byte aligned for float) from / to shared memory
+// 8 consecutive elements (32-byte aligned for float) from shared memory
 __device__ __forceinline__ void lds8(const float *p, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4 *>(p);
     const float4 b = *(reinterpret_cast<const float4 *>(p) + 1);
@@ -80,43 +114,38 @@ __device__ __forceinline__ void lds8(const double *p, double (&v)[8]) {
         v[2 * q] = a.x; v[2 * q + 1] = a.y;
     }
 }
-__device__ __forceinline__ void sts8(float *p, const float (&v)[8]) {
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *(reinterpret_cast<float4 *>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void sts8(double *p, const double (&v)[8]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) *(reinterpret_cast<double2 *>(p) + q) = make_double2(v[2 * q], v[2 * q + 1]);
-}
 
 template <typename T, int LP, bool FCC, bool FAC>
-__global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a) {
+__global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32) grad_kernel(const GradArgs<T> a) {
     extern __shared__ __align__(128) char smem_raw[];
+    typedef typename Fix<T>::bin_t bin_t;
     const int L = a.d.L, N = a.d.N, Tt = a.d.T;
     const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp, lpi = (int)a.ctx.lpi;
     const int64_t tp = a.ctx.tp;
-    const int TB = a.tb, NS = a.nstage;
-    const GradMap mp = grad_map(sizeof(T), L, lpi, sp, nbp, TB, NS, FCC, FAC);
+    const int TB = a.tb, NS = a.nstage, NW = a.nwarps;
+    const GradMap mp = grad_map(sizeof(T), L, lpi, sp, nbp, TB, NS, NW, FCC, FAC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncons = NW * 32;
+    const bool sc_tma = (TB % 4) == 0;             // the per-frame scales ride the ring only when tile starts are 16-byte aligned
 
     T *hh = (T *)(smem_raw + mp.o_hh), *din = (T *)(smem_raw + mp.o_din);
-    T *tH = (T *)(smem_raw + mp.o_tH), *tD = (T *)(smem_raw + mp.o_tD), *Gal = (T *)(smem_raw + mp.o_Gal);
-    int *ylab = (int *)(smem_raw + mp.o_ylab), *order = (int *)(smem_raw + mp.o_order), *lstart = (int *)(smem_raw + mp.o_lstart);
-    uint64_t *full = (uint64_t *)(smem_raw + mp.o_bars), *empty = full + 4;
+    T *Gal = (T *)(smem_raw + mp.o_Gal), *Gf = (T *)(smem_raw + mp.o_Gf);
+    int *ylab = (int *)(smem_raw + mp.o_ylab);
+    uint64_t *full = (uint64_t *)(smem_raw + mp.o_bars), *empty = full + 8;
     char *stages = smem_raw + mp.o_stages;
 
-    const int per = (a.num_tiles + gridDim.x - 1) / gridDim.x;
-    const int q_begin = blockIdx.x * per;
-    const int q_end = min(a.num_tiles, q_begin + per);
+    // balanced contiguous tile ranges
+    const int q_begin = (int)(((int64_t)a.num_tiles * blockIdx.x) / gridDim.x);
+    const int q_end = (int)(((int64_t)a.num_tiles * (blockIdx.x + 1)) / gridDim.x);
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GRAD_CWARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         mbar_fence_init();
     }
     __syncthreads();
 
     // =========================== producer warp: bulk copies into the ring ===========================
-    if (warp == GRAD_CWARPS) {
+    if (warp == NW) {
         if (lane == 0) {
             int cur_n = -1, Tn = 0;
             int it = 0;
@@ -134,9 +163,10 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
                 const int64_t rowc = (int64_t)n * tp + t0;           // first current row
                 const int64_t rowa = rowc - prev;                    // first alpha row fetched
                 const unsigned na = (unsigned)(rows + prev);
+                const unsigned nsc = (unsigned)((rows + 3) / 4 * 4);
                 unsigned bytes = 0;
                 if (FAC) bytes += (unsigned)(sizeof(T) * (na + rows) * sp + sizeof(int) * (na + rows) * nbp);
-                if (FCC) bytes += (unsigned)(sizeof(T) * (na + 2 * rows) * lpi);
+                if (FCC) bytes += (unsigned)(sizeof(T) * ((na + 2 * rows) * lpi + (sc_tma ? nsc : 0)));
                 mbar_arrive_expect_tx(&full[stage], bytes);
                 if (FAC) {
                     bulk_g2s(sb + mp.oA + sizeof(T) * (size_t)(1 - prev) * sp, a.fac_alpha + rowa * sp, (unsigned)(sizeof(T) * na * sp), &full[stage]);
@@ -148,6 +178,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
                     bulk_g2s(sb + mp.oFa + sizeof(T) * (size_t)(1 - prev) * lpi, a.fcc_alpha + rowa * lpi, (unsigned)(sizeof(T) * na * lpi), &full[stage]);
                     bulk_g2s(sb + mp.oFb, a.fcc_beta + rowc * lpi, (unsigned)(sizeof(T) * rows * lpi), &full[stage]);
                     bulk_g2s(sb + mp.oFw, a.ctx.fcc_w + rowc * lpi, (unsigned)(sizeof(T) * rows * lpi), &full[stage]);
+                    if (sc_tma) bulk_g2s(sb + mp.oSc, a.ctx.fcc_scale + rowc, (unsigned)(sizeof(T) * nsc), &full[stage]);
                 }
             }
         }
@@ -155,37 +186,73 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
     }
 
     // =========================== consumer warps =====================================================
-    auto cbar = [&]() { named_bar_sync(1, GRAD_CONSUMERS); };
+    auto cbar = [&]() { named_bar_sync(1, ncons); };
+    const bool narrow = nblk <= 32;                // one 8-position block per lane: everything stays in registers
+    typedef Fix<T> FX;
 
-    // FCC register tile: thread owns rows i0..i0+1, columns j0..j0+3 of G (looped if LP*LP/8 > 256)
-    constexpr int TCOLS = LP / 4;                 // tiles per row of G
-    constexpr int NT = (LP / 2) * TCOLS;          // number of 2x4 tiles
-    constexpr int TPT = (NT + GRAD_CONSUMERS - 1) / GRAD_CONSUMERS;
-    T G[TPT][8];
+    // FCC: per-lane register slice of this warp's G: rows ib*RI.., columns jb*CJ..
+    constexpr int RI = LP / 8, CJ = LP / 4;
+    const int ib = lane >> 2, jb = lane & 3;
+    T G[RI][CJ];
 #pragma unroll
-    for (int q = 0; q < TPT; ++q)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) G[q][e] = T(0);
+        for (int j = 0; j < CJ; ++j) G[i][j] = T(0);
 
+    unsigned long long *galfix = (unsigned long long *)(smem_raw + mp.o_galfix);     // [2][L*L] fixed-point edge sums
+    for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
+
+    bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * GRAD_LBINS;
+    T *acc = (T *)(smem_raw + mp.o_acc) + (size_t)warp * 2 * sp;     // wide mode only: [2][sp] stay / total sums of this warp
     if (FAC) {
-        for (int e = tid; e < L * L; e += GRAD_CONSUMERS) Gal[e] = T(0);
+        for (int l = lane; l < GRAD_LBINS; l += 32) bins[l] = 0;
+        if (!narrow)
+            for (int s = lane; s < 2 * sp; s += 32) acc[s] = T(0);
     }
+    cbar();
 
-    int cur_n = -1;
+    int cur_n = -1, nutt = 0;
     int Tn = 0, Sn = 0;
     T gf = T(0), ga = T(0);
+    // narrow mode: this lane's block of the current utterance.  accH: posterior mass that STAYED into position j,
+    // accQ: all posterior mass at position j (frames >= 1); the moved mass is their difference.
+    T hreg[8], dreg[8], accH[8], accQ[8];
+    int lab[8], labm1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { hreg[j] = dreg[j] = accH[j] = accQ[j] = T(0); lab[j] = L; }
 
-    // scatter the running per-position edge sums of utterance cur_n into the CTA's L x L matrix.
-    // Thread l owns row l of Gal (destination label), so the order of additions is fixed.
+    // Utterance boundary: the per-position edge sums go, as 64-bit fixed point (order-independent), into the CTA's
+    // L x L edge matrix of this utterance; after one barrier they are scaled by the utterance's upstream gradient and
+    // added to Gal by the thread that owns the element.  Two matrices alternate so one barrier per boundary is enough.
     auto flush_fac = [&]() {
         if (!FAC || cur_n < 0) return;
-        if (tid < L) {
-            for (int k = lstart[tid]; k < lstart[tid + 1]; ++k) {
-                const int s = order[k];
-                Gal[tid * L + tid] += tH[s];
-                if (s >= 1) Gal[tid * L + ylab[s - 1]] += tD[s];
+        unsigned long long *gfix = galfix + (size_t)(nutt & 1) * L * L;
+        if (narrow) {
+            if (lane < nblk) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (lab[j] < L) {
+                        const int prevlab = j ? lab[j ? j - 1 : 0] : labm1;
+                        atomicAdd(&gfix[lab[j] * L + lab[j]], FX::edge_fix(accH[j]));
+                        if (lane * 8 + j >= 1) atomicAdd(&gfix[lab[j] * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
+                    }
+                    accH[j] = accQ[j] = T(0);
+                }
+            }
+        } else {
+            for (int s = lane; s < Sn; s += 32) {
+                const int l = ylab[s];
+                atomicAdd(&gfix[l * L + l], FX::edge_fix(acc[s]));
+                if (s >= 1) atomicAdd(&gfix[l * L + ylab[s - 1]], FX::edge_fix(acc[sp + s] - acc[s]));
+                acc[s] = T(0); acc[sp + s] = T(0);
             }
         }
+        cbar();
+        for (int e = tid; e < L * L; e += ncons) {
+            Gal[e] += ga * FX::edge_unfix(gfix[e]);
+            gfix[e] = 0;
+        }
+        ++nutt;
     };
 
     int it = 0;
@@ -195,9 +262,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
         const int t0 = (q % a.tiles_t) * TB;
         const int TBt = min(TB, Tt - t0);         // frames in this tile
         if (n != cur_n) {
-            cbar();                                // every warp is done with the previous utterance's tiles
             flush_fac();
-            cbar();
             cur_n = n;
             Tn = (int)a.ctx.il[n];
             gf = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
@@ -205,231 +270,214 @@ __global__ void __launch_bounds__(GRAD_THREADS) grad_kernel(const GradArgs<T> a)
             if (FAC) {
                 Sn = (int)a.ctx.tl[n];
                 const int64_t *yn = a.y + (int64_t)n * a.y_s0;
-                for (int s = tid; s < sp; s += GRAD_CONSUMERS) {
-                    int lab = -1;
-                    if (s < Sn) { lab = (int)yn[(int64_t)s * a.y_s1]; lab = max(0, min(L - 1, lab)); }
-                    ylab[s] = lab;
-                    hh[s] = a.ctx.fac_hd[(int64_t)n * sp + s];
-                    din[s] = (s >= 1) ? a.ctx.fac_hd[((int64_t)N + n) * sp + s - 1] : T(0);
-                    tH[s] = T(0);
-                    tD[s] = T(0);
-                }
-                cbar();
-                // CSR by label; positions ascending inside a label (fixed summation order).
-                // Thread l counts, thread 0 scans the L counts, thread l fills its own segment.
-                int cnt = 0;
-                if (tid < L)
-                    for (int s = 0; s < Sn; ++s) cnt += (ylab[s] == tid);
-                if (tid < L) lstart[tid + 1] = cnt;
-                cbar();
-                if (tid == 0) {
-                    int acc = 0;
-                    lstart[0] = 0;
-                    for (int l = 0; l < L; ++l) { acc += lstart[l + 1]; lstart[l + 1] = acc; }
-                }
-                cbar();
-                if (tid < L) {
-                    int pos = lstart[tid];
-                    for (int s = 0; s < Sn; ++s) if (ylab[s] == tid) order[pos++] = s;
+                if (narrow) {
+                    // every warp loads its own copy of the utterance constants: no barrier
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int s = lane * 8 + j;
+                        lab[j] = L; hreg[j] = T(0); dreg[j] = T(0);
+                        if (s < Sn) {
+                            lab[j] = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
+                            hreg[j] = a.ctx.fac_hd[(int64_t)n * sp + s];
+                            if (s >= 1) dreg[j] = a.ctx.fac_hd[((int64_t)N + n) * sp + s - 1];
+                        }
+                    }
+                    labm1 = __shfl_up_sync(ASG_FULL_MASK, lab[7], 1);
+                } else {
+                    cbar();                        // the previous utterance's frames are done everywhere
+                    for (int s = tid; s < sp; s += ncons) {
+                        int lb = L;
+                        if (s < Sn) lb = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
+                        ylab[s] = lb;
+                        hh[s] = a.ctx.fac_hd[(int64_t)n * sp + s];
+                        din[s] = (s >= 1) ? a.ctx.fac_hd[((int64_t)N + n) * sp + s - 1] : T(0);
+                    }
+                    cbar();
                 }
             }
-            cbar();
         }
         const int rows_valid = max(0, min(TBt, Tn - t0));   // frames t0 .. t0+rows_valid-1 are inside the utterance
         char *sb = stages + (size_t)stage * mp.stage_bytes;
-        T *sA = (T *)(sb + mp.oA), *sB = (T *)(sb + mp.oB), *sBnd = (T *)(sb + mp.oBnd), *sZb = (T *)(sb + mp.oZb);
-        int *sEa = (int *)(sb + mp.oEa), *sEb = (int *)(sb + mp.oEb);
-        T *sFa = (T *)(sb + mp.oFa), *sFb = (T *)(sb + mp.oFb), *sFw = (T *)(sb + mp.oFw);
+        const T *sA = (const T *)(sb + mp.oA), *sB = (const T *)(sb + mp.oB);
+        const int *sEa = (const int *)(sb + mp.oEa), *sEb = (const int *)(sb + mp.oEb);
+        const T *sFa = (const T *)(sb + mp.oFa), *sFb = (const T *)(sb + mp.oFb), *sFw = (const T *)(sb + mp.oFw), *sSc = (const T *)(sb + mp.oSc);
 
         mbar_wait(&full[stage], use & 1);
 
-        // ================= phase 1: posteriors, one warp per frame ================================
         // smem row r of the alpha arrays = frame t0-1+r (r = 0 is the halo); beta arrays: row r-1 = frame t0-1+r
-        if (rows_valid > 0) {
-            const int r_lo = t0 > 0 ? 0 : 1;
-            for (int r = r_lo + warp; r <= rows_valid; r += GRAD_CWARPS) {
-                const int t = t0 - 1 + r;
-                const bool iscur = r >= 1;
-                const bool isprev = r < rows_valid;
-                if (FAC) {
-                    const bool single = nblk <= 32;
-                    T zsum = T(0);
-                    int cmax = INT_MIN;
-                    T keep[8];
-                    int keepc = INT_MIN;
-                    for (int b0 = 0; b0 < nblk; b0 += 32) {
-                        const int b = b0 + lane;
-                        if (b >= nblk) continue;
-                        T av[8];
-                        lds8(sA + (size_t)r * sp + b * 8, av);
-                        const int ea = sEa[r * nbp + b];
-                        if (isprev) {
-                            // the block's last value expressed in the NEXT block's exponent (what position 8(b+1) sees on its left)
-                            const int ean = (b + 1 < nblk) ? sEa[r * nbp + b + 1] : ea;
-                            sBnd[r * nbp + b] = av[7] * Num<T>::exp2i(ea - ean);
-                        }
-                        if (iscur) {
-                            T bv[8];
-                            lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
-                            const int eb = sEb[(r - 1) * nbp + b];
-                            T pm = T(0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) { bv[j] *= av[j]; pm = tmax(pm, bv[j]); }
-                            const int c = (pm > T(0)) ? ea + eb : INT_MIN;     // a block without mass is ignored
-                            cmax = max(cmax, c);
-                            if (single) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) keep[j] = bv[j];
-                                keepc = c;
-                            } else {
-                                sts8(sB + (size_t)(r - 1) * sp + b * 8, bv);
-                                sEb[(r - 1) * nbp + b] = c;
-                            }
-                        }
-                    }
-                    if (iscur) {
-                        cmax = __reduce_max_sync(ASG_FULL_MASK, cmax);
-                        // bring every block to the frame's common exponent, sum the frame
-                        if (single) {
-                            if (lane < nblk) {
-                                T wgt = T(0);
-                                if (keepc != INT_MIN && keepc - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(keepc - cmax);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { keep[j] *= wgt; zsum += keep[j]; }
-                                sts8(sB + (size_t)(r - 1) * sp + lane * 8, keep);
-                            }
-                        } else {
-                            __syncwarp();
-                            for (int b0 = 0; b0 < nblk; b0 += 32) {
-                                const int b = b0 + lane;
-                                if (b >= nblk) continue;
-                                const int c = sEb[(r - 1) * nbp + b];
-                                T wgt = T(0);
-                                if (c != INT_MIN && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax);
-                                T pv[8];
-                                lds8(sB + (size_t)(r - 1) * sp + b * 8, pv);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { pv[j] *= wgt; zsum += pv[j]; }
-                                sts8(sB + (size_t)(r - 1) * sp + b * 8, pv);
-                            }
-                        }
-                        zsum = warp_sum(zsum);
-                        if (lane == 0) sZb[r - 1] = (zsum > T(0)) ? ga / zsum : T(0);
-                    }
-                }
-                if (FCC && iscur) {
-                    T al0 = T(0), al1 = T(0), be0 = T(0), be1 = T(0), w0 = T(0), w1 = T(0);
-                    if (lane < lpi) { al0 = sFa[r * lpi + lane]; be0 = sFb[(r - 1) * lpi + lane]; w0 = sFw[(r - 1) * lpi + lane]; }
-                    if (LP > 32 && lane + 32 < lpi) {
-                        al1 = sFa[r * lpi + lane + 32]; be1 = sFb[(r - 1) * lpi + lane + 32]; w1 = sFw[(r - 1) * lpi + lane + 32];
-                    }
-                    const T sc = __ldg(a.ctx.fcc_scale + (int64_t)n * tp + t);
-                    const T g0 = al0 * be0, g1 = al1 * be1;
-                    const T Z = warp_sum(g0 + g1);
-                    const T inv = (Z > T(0)) ? gf / Z : T(0);
-                    const T winv = (t >= 1) ? inv * sc : T(0);          // no incoming edge at frame 0
-                    if (lane < lpi) { sFb[(r - 1) * lpi + lane] = g0 * inv; sFw[(r - 1) * lpi + lane] = w0 * winv; }
-                    if (LP > 32 && lane + 32 < lpi) { sFb[(r - 1) * lpi + lane + 32] = g1 * inv; sFw[(r - 1) * lpi + lane + 32] = w1 * winv; }
-                }
+        for (int r = 1 + warp; r <= TBt; r += NW) {
+            const int t = t0 - 1 + r;
+            T *gx_row = a.grad_x + ((int64_t)t * N + n) * L;
+            if (r > rows_valid) {                       // padding frame: exact zeros
+                for (int l = lane; l < L; l += 32) gx_row[l] = T(0);
+                continue;
             }
-        }
-        cbar();
-
-        // ================= phase 2 =================================================================
-        // (a) grad_x rows: FCC posterior + label gather of the FAC posterior; each element written exactly once
-        for (int p = tid; p < TBt * L; p += GRAD_CONSUMERS) {
-            const int r = p / L, l = p - r * L;
-            T val = T(0);
-            if (r < rows_valid) {
-                if (FCC) val = sFb[r * lpi + l];
-                if (FAC) {
-                    T acc = T(0);
-                    const T *row = sB + (size_t)r * sp;
-                    for (int k = lstart[l]; k < lstart[l + 1]; ++k) acc += row[order[k]];
-                    val += acc * sZb[r];
-                }
-            }
-            a.grad_x[((int64_t)(t0 + r) * N + n) * L + l] = val;
-        }
-        if (rows_valid > 0) {
-            // (b) per-position edge posteriors, summed over the tile's frames (thread <-> position: fixed order)
+            // ---------------- FAC: posterior, label scatter, edge posteriors ----------------------
             if (FAC) {
-                for (int s = tid; s < Sn; s += GRAD_CONSUMERS) {
-                    T accH = T(0), accD = T(0);
-                    const T hs = hh[s], ds = din[s];
-                    const bool edge = (s & 7) == 0;
-                    const int lo = (s > 0) ? (edge ? (s >> 3) - 1 : s - 1) : 0;
-                    for (int r = 1; r <= rows_valid; ++r) {
-                        if (t0 - 1 + r < 1) continue;                       // frame 0 has no incoming edge
-                        const T post = sB[(size_t)(r - 1) * sp + s] * sZb[r - 1];
-                        const T stay = hs * sA[(size_t)(r - 1) * sp + s];
-                        const T lft = (edge && s > 0) ? sBnd[(r - 1) * nbp + lo] : sA[(size_t)(r - 1) * sp + lo];
-                        const T move = ds * lft;
-                        const T den = stay + move;
-                        if (den > T(0)) {
-                            if (den < -Num<T>::neg_inf()) {
-                                const T pd = post / den;                    // post is proportional to den: no overflow for tiny den
-                                accH = fma(pd, stay, accH);
-                                accD = fma(pd, move, accD);
-                            } else {
-                                accD += post;                               // the aligned neighbour overflowed: it dominates
-                            }
-                        }
-                    }
-                    tH[s] += accH;
-                    tD[s] += accD;
-                }
-            }
-            // (c) FCC transition gradient: G += w_t (x) alpha_{t-1}
-            if (FCC) {
+                if (narrow) {
+                    const int lb8 = min(lane, nblk - 1) * 8;          // idle lanes re-read the last block (weight 0)
+                    const int le = min(lane, nblk - 1);
+                    const bool act = lane < nblk;
+                    T av[8], bv[8];
+                    lds8(sA + r * sp + lb8, av);
+                    lds8(sB + (r - 1) * sp + lb8, bv);
+                    const int ea = sEa[r * nbp + le], eb = sEb[(r - 1) * nbp + le];
+                    // alpha and beta mantissas are normalised separately (block maxima in [1,2)), so where one peaks the
+                    // other can be ~2^-100: the products carry a constant 2^120 (2^960) so they stay normal numbers
 #pragma unroll
-                for (int qq = 0; qq < TPT; ++qq) {
-                    const int tile = tid + qq * GRAD_CONSUMERS;
-                    if (tile < NT) {
-                        const int i0 = (tile / TCOLS) * 2, j0 = (tile % TCOLS) * 4;
-                        if (i0 < lpi && j0 < lpi) {
-                            for (int r = 1; r <= rows_valid; ++r) {
-                                if (t0 - 1 + r < 1) continue;
-                                const T wa = sFw[(r - 1) * lpi + i0], wb = sFw[(r - 1) * lpi + i0 + 1];
-                                const T *pp = sFa + (r - 1) * lpi + j0;
-                                const T p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
-                                G[qq][0] = fma(wa, p0, G[qq][0]); G[qq][1] = fma(wa, p1, G[qq][1]);
-                                G[qq][2] = fma(wa, p2, G[qq][2]); G[qq][3] = fma(wa, p3, G[qq][3]);
-                                G[qq][4] = fma(wb, p0, G[qq][4]); G[qq][5] = fma(wb, p1, G[qq][5]);
-                                G[qq][6] = fma(wb, p2, G[qq][6]); G[qq][7] = fma(wb, p3, G[qq][7]);
+                    for (int j = 0; j < 8; ++j) bv[j] = av[j] * (bv[j] * Num<T>::prod_scale());
+                    const T pm = tmax(tmax(tmax(bv[0], bv[1]), tmax(bv[2], bv[3])), tmax(tmax(bv[4], bv[5]), tmax(bv[6], bv[7])));
+                    const T ps = ((bv[0] + bv[1]) + (bv[2] + bv[3])) + ((bv[4] + bv[5]) + (bv[6] + bv[7]));
+                    const int c = (act && pm > T(0)) ? ea + eb : INT_MIN;    // a block without mass is ignored
+                    const int cmax = __reduce_max_sync(ASG_FULL_MASK, c);
+                    T wgt = T(0);
+                    if (c != INT_MIN && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax);
+                    const T Z = warp_sum(ps * wgt);
+                    const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
+                    const T kq = wgt * FX::kPost;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bv[j] = (bv[j] * invZ) * kq;                   // posterior of position 8*lane+j, in fixed-point units
+                        FX::add(&bins[lab[j]], FX::to_fix(bv[j]));
+                    }
+                    if (t >= 1) {
+                        T pv[8];
+                        lds8(sA + (r - 1) * sp + lb8, pv);
+                        const int ep = sEa[(r - 1) * nbp + le];
+                        // the left neighbour's last value, expressed in this block's exponent (bounded so den stays finite)
+                        T left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
+                        const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
+                        left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep, Num<T>::kMaxShift - 8));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const T stay = hreg[j] * pv[j];
+                            const T den = fma(dreg[j], j ? pv[j ? j - 1 : 0] : left, stay);
+                            // den == 0 implies a zero posterior, so the floor only guards 0/0
+                            const T fs = fast_div(stay, tmax(den, Num<T>::tiny()));     // share of the mass that stayed (<= 1)
+                            accH[j] = fma(bv[j], fs, accH[j]);
+                            accQ[j] += bv[j];
+                        }
+                    }
+                } else {
+                    // wide targets (S > 256): several blocks per lane; three passes over the frame, sums parked in shared memory
+                    int cmax = INT_MIN;
+                    for (int b = lane; b < nblk; b += 32) {
+                        T av[8], bv[8];
+                        lds8(sA + (size_t)r * sp + b * 8, av);
+                        lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
+                        T pm = T(0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pm = tmax(pm, av[j] * (bv[j] * Num<T>::prod_scale()));
+                        if (pm > T(0)) cmax = max(cmax, sEa[r * nbp + b] + sEb[(r - 1) * nbp + b]);
+                    }
+                    cmax = __reduce_max_sync(ASG_FULL_MASK, cmax);
+                    T zs = T(0);
+                    for (int b = lane; b < nblk; b += 32) {
+                        T av[8], bv[8];
+                        lds8(sA + (size_t)r * sp + b * 8, av);
+                        lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
+                        const int c = sEa[r * nbp + b] + sEb[(r - 1) * nbp + b];
+                        T pm = T(0), ps = T(0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const T p = av[j] * (bv[j] * Num<T>::prod_scale()); pm = tmax(pm, p); ps += p; }
+                        if (pm > T(0) && c - cmax >= -Num<T>::kMaxShift) zs += ps * Num<T>::exp2i(c - cmax);
+                    }
+                    const T Z = warp_sum(zs);
+                    const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
+                    for (int b = lane; b < nblk; b += 32) {
+                        T av[8], bv[8];
+                        lds8(sA + (size_t)r * sp + b * 8, av);
+                        lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
+                        const int c = sEa[r * nbp + b] + sEb[(r - 1) * nbp + b];
+                        T pm = T(0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * (bv[j] * Num<T>::prod_scale())) * invZ; pm = tmax(pm, bv[j]); }
+                        T wgt = T(0);
+                        if (pm > T(0) && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax) * FX::kPost;
+                        if (wgt == T(0)) continue;
+                        T pv[8], left = T(0);
+                        if (t >= 1) {
+                            lds8(sA + (size_t)(r - 1) * sp + b * 8, pv);
+                            if (b > 0)
+                                left = sA[(size_t)(r - 1) * sp + b * 8 - 1] *
+                                       Num<T>::exp2i(min(sEa[(r - 1) * nbp + b - 1] - sEa[(r - 1) * nbp + b], Num<T>::kMaxShift - 8));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const T post = bv[j] * wgt;
+                            const int s = b * 8 + j;
+                            FX::add(&bins[ylab[s]], FX::to_fix(post));
+                            if (t >= 1) {
+                                const T stay = hh[s] * pv[j];
+                                const T den = fma(din[s], j ? pv[j ? j - 1 : 0] : left, stay);
+                                const T fs = fast_div(stay, tmax(den, Num<T>::tiny()));
+                                acc[s] = fma(post, fs, acc[s]);
+                                acc[sp + s] += post;
                             }
                         }
                     }
                 }
+                __syncwarp();
             }
+            // ---------------- FCC: posterior, outer product; grad_x row -----------------------------
+            T g0 = T(0), g1 = T(0);
+            if (FCC) {
+                T al0 = T(0), al1 = T(0), be0 = T(0), be1 = T(0);
+                if (lane < lpi) { al0 = sFa[r * lpi + lane]; be0 = sFb[(r - 1) * lpi + lane]; }
+                if (LP > 32 && lane + 32 < lpi) { al1 = sFa[r * lpi + lane + 32]; be1 = sFb[(r - 1) * lpi + lane + 32]; }
+                g0 = al0 * be0; g1 = al1 * be1;
+                const T Z = warp_sum(g0 + g1);
+                const T inv = (Z > T(0)) ? gf / Z : T(0);
+                g0 *= inv; g1 *= inv;
+                if (t >= 1) {                                  // no incoming edge at frame 0
+                    const T winv = inv * (sc_tma ? sSc[r - 1] : a.ctx.fcc_scale[(int64_t)n * tp + t]);
+                    T wv[RI], pv[CJ];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) wv[i] = sFw[(r - 1) * lpi + ib * RI + i] * winv;
+#pragma unroll
+                    for (int j = 0; j < CJ; ++j) pv[j] = sFa[(r - 1) * lpi + jb * CJ + j];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int j = 0; j < CJ; ++j) G[i][j] = fma(wv[i], pv[j], G[i][j]);
+                }
+            }
+            if (FAC) {
+                const T gs = ga * FX::kInvPost;
+                if (lane < L) { g0 = fma(gs, FX::from_fix(bins[lane]), g0); bins[lane] = 0; }
+                if (LP > 32 && lane + 32 < L) { g1 = fma(gs, FX::from_fix(bins[lane + 32]), g1); bins[lane + 32] = 0; }
+                __syncwarp();
+            }
+            if (lane < L) gx_row[lane] = g0;
+            if (LP > 32 && lane + 32 < L) gx_row[lane + 32] = g1;
         }
-        // release the stage: this thread's generic-proxy accesses are ordered before the next bulk copy
-        fence_proxy_async();
+        // release the stage (read-only for the consumers)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
     }
-    cbar();
     flush_fac();
     cbar();
 
-    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC) -------------------------------------
-    T *part = a.partials + (size_t)blockIdx.x * L * L;
+    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC): warps add their G slices in order ----
+    if (FCC) {
+        for (int w = 0; w < NW; ++w) {
+            if (warp == w) {
 #pragma unroll
-    for (int qq = 0; qq < TPT; ++qq) {
-        const int tile = tid + qq * GRAD_CONSUMERS;
-        if (tile < NT) {
-            const int i0 = (tile / TCOLS) * 2, j0 = (tile % TCOLS) * 4;
+                for (int i = 0; i < RI; ++i)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int i = i0 + (e >> 2), j = j0 + (e & 3);
-                if (i < L && j < L) {
-                    T v = T(0);
-                    if (FCC) v = a.ctx.ehat[i * L + j] * G[qq][e];
-                    if (FAC) v += Gal[i * L + j];
-                    part[i * L + j] = v;
-                }
+                    for (int j = 0; j < CJ; ++j) {
+                        const int gi = ib * RI + i, gj = jb * CJ + j;
+                        if (gi < L && gj < L) Gf[gi * L + gj] += G[i][j];
+                    }
             }
+            cbar();
         }
+    }
+    T *part = a.partials + (size_t)blockIdx.x * L * L;
+    for (int e = tid; e < L * L; e += ncons) {
+        T v = Gal[e];
+        if (FCC) v += a.ctx.ehat[e] * Gf[e];
+        part[e] = v;
     }
 }
 
@@ -461,13 +509,13 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const T *partials, i
 // =============================================================================================
 int grad_grid_size(int device) {
     static int sms[64] = {0};
-    if (device < 0 || device >= 64) return 148 * 2;
+    if (device < 0 || device >= 64) return 148;
     if (!sms[device]) {
         int v = 0;
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
         sms[device] = v;
     }
-    return sms[device] * 2;
+    return sms[device];
 }
 
 template <typename T, int LP, bool FCC, bool FAC>
@@ -476,23 +524,24 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     const int L = a.d.L, sp = (int)a.ctx.sp, nbp = (int)a.ctx.nbp, lpi = (int)a.ctx.lpi;
     int device = 0;
     cudaGetDevice(&device);
-    // frames per tile / ring depth: the largest that lets two CTAs share an SM, else whatever fits
-    static const int cand[][2] = {{16, 2}, {8, 2}, {4, 2}, {2, 2}, {1, 2}, {4, 1}, {2, 1}, {1, 1}};
-    int tb = 0, ns = 0;
+    // (frames per tile, ring depth, consumer warps): one persistent CTA per SM, as much in flight as fits
+    static const int cand[][3] = {{16, 4, 8}, {16, 3, 8}, {8, 4, 8}, {8, 3, 8}, {8, 2, 8}, {4, 3, 4}, {4, 2, 4},
+                                  {2, 2, 2}, {1, 2, 2}, {1, 2, 1}, {1, 1, 1}};
+    int tb = 0, ns = 0, nw = 0;
     size_t bytes = 0;
-    int force_tb = 0;
+    int force_tb = 0, force_ns = 0;
     if (const char *env = getenv("ASG_GRAD_TB")) force_tb = atoi(env);
-    for (int pass = 0; pass < 2 && !tb; ++pass) {
-        const size_t limit = pass == 0 ? 112 * 1024 : 227 * 1024;
-        for (auto &c : cand) {
-            if (force_tb && c[0] != force_tb) continue;
-            const size_t b = grad_map(sizeof(T), L, lpi, sp, nbp, c[0], c[1], FCC, FAC).total;
-            if (b <= limit) { tb = c[0]; ns = c[1]; bytes = b; break; }
-        }
+    if (const char *env = getenv("ASG_GRAD_NS")) force_ns = atoi(env);
+    for (auto &c : cand) {
+        if (force_tb && c[0] != force_tb) continue;
+        if (force_ns && c[1] != force_ns) continue;
+        const size_t b = grad_map(sizeof(T), L, lpi, sp, nbp, c[0], c[1], c[2], FCC, FAC).total;
+        if (b <= 227 * 1024) { tb = c[0]; ns = c[1]; nw = c[2]; bytes = b; break; }
     }
     if (!tb) return cudaErrorInvalidValue;
     a.tb = tb;
     a.nstage = ns;
+    a.nwarps = nw;
     a.tiles_t = (a.d.T + tb - 1) / tb;
     a.num_tiles = a.tiles_t * a.d.N;
     cudaError_t e = cudaFuncSetAttribute(grad_kernel<T, LP, FCC, FAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -501,7 +550,7 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     if (grid > a.num_tiles) grid = a.num_tiles;
     {
         LaunchScope ls(K_GRAD, st);
-        grad_kernel<T, LP, FCC, FAC><<<grid, GRAD_THREADS, bytes, st>>>(a);
+        grad_kernel<T, LP, FCC, FAC><<<grid, (nw + 1) * 32, bytes, st>>>(a);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const int LL = L * L;

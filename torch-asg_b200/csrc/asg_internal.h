@@ -73,6 +73,7 @@ template <typename T> struct GradArgs {
     T *partials;                // [grid, L*L] per-CTA partial transition gradients
     int tb;                     // frames per tile
     int nstage;                 // depth of the shared-memory tile ring
+    int nwarps;                 // consumer warps per CTA
     int tiles_t;                // ceil(T / tb)
     int num_tiles;              // tiles_t * N
 };
