@@ -135,13 +135,54 @@ __device__ __forceinline__ T transition_max(const T *A, int64_t s0, int64_t s1, 
     return (m > Num<T>::neg_inf()) ? m : T(0);
 }
 
+template <typename T, int NE> struct RowRegs;
+// dot product of a register-resident row of E with the state vector in shared memory.
+// float: packed FFMA2 (two fp32 FMAs per instruction, sm_100) on register pairs; double: scalar FMAs.
+template <int NE> struct RowRegs<float, NE> {
+    float2 e[NE / 2];
+    __device__ __forceinline__ void set(int j, float v) { if (j & 1) e[j >> 1].y = v; else e[j >> 1].x = v; }
+    // p: NE contiguous floats, 8-byte aligned (16-byte aligned when VEC4)
+    template <bool VEC4> __device__ __forceinline__ float dot(const float *p) const {
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        if (VEC4) {
+#pragma unroll
+            for (int i = 0; i < NE / 4; ++i) {
+                const float4 q = *reinterpret_cast<const float4 *>(p + 4 * i);
+                if (i & 1) { a2 = __ffma2_rn(e[2 * i], make_float2(q.x, q.y), a2); a3 = __ffma2_rn(e[2 * i + 1], make_float2(q.z, q.w), a3); }
+                else { a0 = __ffma2_rn(e[2 * i], make_float2(q.x, q.y), a0); a1 = __ffma2_rn(e[2 * i + 1], make_float2(q.z, q.w), a1); }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NE / 2; ++i) {
+                const float2 q = *reinterpret_cast<const float2 *>(p + 2 * i);
+                if (i & 1) a1 = __ffma2_rn(e[i], q, a1); else a0 = __ffma2_rn(e[i], q, a0);
+            }
+        }
+        a0 = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
+        return a0.x + a0.y;
+    }
+};
+template <int NE> struct RowRegs<double, NE> {
+    double e[NE];
+    __device__ __forceinline__ void set(int j, double v) { e[j] = v; }
+    template <bool VEC4> __device__ __forceinline__ double dot(const double *p) const {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NE; j += 4) {
+            a0 = fma(e[j], p[j], a0); a1 = fma(e[j + 1], p[j + 1], a1);
+            if (j + 2 < NE) { a2 = fma(e[j + 2], p[j + 2], a2); a3 = fma(e[j + 3], p[j + 3], a3); }
+        }
+        return (a0 + a1) + (a2 + a3);
+    }
+};
+
 template <typename T, int LP, bool BETA>
 __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) {
     constexpr bool FULL = (LP >= 32);
     constexpr int REM = FULL ? LP - 32 : LP;                      // rows handled with a column split
     constexpr int RP = REM <= 8 ? 8 : (REM <= 16 ? 16 : 32);
     constexpr int CH = 32 / RP;                                   // column chunks
-    constexpr int CL = LP / CH;                                   // columns per chunk
+    constexpr int CL = LP / CH;                                   // columns per chunk (even)
     constexpr int RBASE = FULL ? 32 : 0;
     const int L = a.d.L;
     const int lpi = (int)a.ctx.lpi;
@@ -152,114 +193,124 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
 
     // ---- transition matrix -> registers (real domain, max-normalised) -------------------------
     const T R = transition_max(a.A, a.A_s0, a.A_s1, L, lane);
-    T E1[FULL ? LP : 1];
-    T E2[REM > 0 ? CL : 1];
+    constexpr int NE1 = FULL ? LP : 4, NE2 = (REM > 0) ? CL : 4;
+    RowRegs<T, NE1> E1;
+    RowRegs<T, NE2> E2;
     if (FULL) {
 #pragma unroll
         for (int j = 0; j < LP; ++j)
-            E1[j] = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, j, L, R);
+            E1.set(j, BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, j, L, R));
     }
     if (REM > 0) {
 #pragma unroll
         for (int c = 0; c < CL; ++c) {
             const int j = cc * CL + c;
-            E2[c] = !has2 ? T(0)
-                          : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j, L, R));
+            E2.set(c, !has2 ? T(0)
+                            : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j, L, R)));
         }
     }
     if (!BETA && n == 0) {   // publish E for the gradient assembly
         for (int e = lane; e < L * L; e += 32) a.ctx.ehat[e] = ehat_of(a.A, a.A_s0, a.A_s1, e / L, e % L, L, R);
     }
     if (!BETA && lane == 0) a.ctx.il[n] = Tn;
+    if (Tn <= 0) {
+        if (lane == 0 && BETA && a.full_scores) a.full_scores[n] = T(0);
+        return;
+    }
 
-    T *state = BETA ? a.fcc_beta : a.fcc_alpha;
-    int ready = 0;
+    // state rows of this utterance are contiguous: walk them with pointers (forwards for alpha, backwards for beta)
+    const int64_t step = BETA ? -(int64_t)lpi : (int64_t)lpi;
+    const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
+    T *st1 = (BETA ? a.fcc_beta : a.fcc_alpha);
+    const bool store = st1 != nullptr;
+    T *stw = BETA ? a.ctx.fcc_w : nullptr;
+    T *scp = a.ctx.fcc_scale + row0;
+    const bool wr1 = FULL && lane < lpi, wr2 = has2 && cc == 0 && row2 < lpi;
+    const int o1 = lane, o2 = row2;
+    if (store) { st1 += row0 * lpi; if (BETA) stw += row0 * lpi; }
+
     int esum = 0;
-    int cur = 0;
-    T v1 = T(0), v2 = T(0);     // this lane's rows of the current state vector
-    T last_w1 = T(0), last_w2 = T(0);
+    T sc = T(1);                // power of two applied at the NEXT step (from the maximum of the vector that feeds it)
+    int e_next = 0;
+    T f1 = T(0), f2 = T(0);     // this lane's rows of the vector that feeds the next mat-vec (alpha: P, beta: u o Q)
 
-    for (int k = 0; k < Tn; ++k) {
-        const int t = BETA ? (Tn - 1 - k) : k;
-        if (k >= ready) {
-            while ((ready = ld_volatile_s32(&sm.produced)) <= k) __nanosleep(20);
-            __threadfence_block();
+    auto wait_batch = [&](int k) {      // frames k .. k+FB-1 (or up to Tn) must be in the ring
+        const int need = min(k + FB, Tn);
+        while (ld_volatile_s32(&sm.produced) < need) __nanosleep(20);
+        __threadfence_block();
+    };
+    auto publish = [&](T v1, T v2, T w1, T w2, T *pout, T applied) {
+        if (FULL) pout[lane] = BETA ? w1 : v1;
+        if (has2 && cc == 0) pout[row2] = BETA ? w2 : v2;
+        if (store) {
+            if (wr1) { st_stream(st1 + o1, v1); if (BETA) st_stream(stw + o1, w1); }
+            if (wr2) { st_stream(st1 + o2, v2); if (BETA) st_stream(stw + o2, w2); }
+            st1 += step;
+            if (BETA) stw += step;
+        }
+        if (!BETA) { if (lane == 0) *scp = applied; scp += 1; }
+        // the next step's scale: exact power of two from one REDUX over the feeding vector (off the dependent chain)
+        const T M = Num<T>::warp_max_nonneg(tmax(BETA ? w1 : v1, BETA ? w2 : v2));
+        Num<T>::pow2_norm(M, sc, e_next);
+    };
+
+    // ---- frame 0 --------------------------------------------------------------------------------
+    wait_batch(0);
+    if (!FULL) { for (int l = lane; l < LP; l += 32) { sm.pvec[0][l] = T(0); sm.pvec[1][l] = T(0); } __syncwarp(); }
+    {
+        const T *urow = sm.uring;
+        const T u1 = FULL ? urow[lane] : T(0);
+        const T u2 = has2 ? urow[row2] : T(0);
+        T v1, v2;
+        if (BETA) { v1 = (FULL && lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
+        else { v1 = u1; v2 = u2; }
+        f1 = BETA ? v1 * u1 : v1; f2 = BETA ? v2 * u2 : v2;
+        publish(v1, v2, f1, f2, sm.pvec[1], T(1));
+        __syncwarp();
+    }
+    // ---- frames 1 .. Tn-1 -------------------------------------------------------------------------
+    auto one_step = [&](int k, const T *pin, T *pout) {
+        if ((k & (FB - 1)) == 0) {
+            if (lane == 0) st_volatile_s32(&sm.consumed, k);      // frames < k are done: their ring slots may be refilled
+            wait_batch(k);
         }
         const T *urow = sm.uring + (size_t)(k % RING) * LP;
         const T u1 = FULL ? urow[lane] : T(0);
         const T u2 = has2 ? urow[row2] : T(0);
-        T sc = T(1);
-        if (k == 0) {
-            if (BETA) { v1 = (FULL && lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
-            else { v1 = u1; v2 = u2; }
-        } else {
-            // ---- z = E p (alpha) / E^T w (beta) ------------------------------------------------
-            const T *pv = sm.pvec[cur];
-            T z2 = T(0);
-            if (REM > 0) {
-                T acc0 = T(0), acc1 = T(0);
+        const T applied = sc;
+        esum += e_next;
+        T z2 = T(0);
+        if (REM > 0) {
+            z2 = E2.template dot<false>(pin + cc * CL);
 #pragma unroll
-                for (int c = 0; c < CL; c += 2) {
-                    acc0 = fma(E2[c], pv[cc * CL + c], acc0);
-                    if (c + 1 < CL) acc1 = fma(E2[c + 1], pv[cc * CL + c + 1], acc1);
-                }
-                z2 = acc0 + acc1;
-#pragma unroll
-                for (int o = RP; o < 32; o <<= 1) z2 += __shfl_xor_sync(ASG_FULL_MASK, z2, o);
-            }
-            T z1 = T(0);
-            if (FULL) {
-                T acc[4] = {T(0), T(0), T(0), T(0)};
-#pragma unroll
-                for (int j = 0; j < LP; ++j) acc[j & 3] = fma(E1[j], pv[j], acc[j & 3]);
-                z1 = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-            }
-            if (BETA) { v1 = z1; v2 = z2; }
-            else { v1 = z1 * u1; v2 = z2 * u2; }
-            const T M = Num<T>::warp_max_nonneg(tmax(v1, v2));
-            int e;
-            Num<T>::pow2_norm(M, sc, e);
-            v1 *= sc; v2 *= sc;
-            esum += e;
+            for (int o = RP; o < 32; o <<= 1) z2 += __shfl_xor_sync(ASG_FULL_MASK, z2, o);
         }
-        // ---- publish the new state ---------------------------------------------------------------
-        const int64_t base = ((int64_t)n * tp + t) * lpi;
-        T w1 = v1, w2 = v2;                       // what feeds the next mat-vec
-        if (BETA) { w1 = v1 * u1; w2 = v2 * u2; }
-        if (FULL) {
-            sm.pvec[cur ^ 1][lane] = w1;
-            if (lane < lpi && state) {
-                st_stream(state + base + lane, v1);
-                if (BETA) st_stream(a.ctx.fcc_w + base + lane, w1);
-            }
-        }
-        if (has2 && cc == 0) {
-            sm.pvec[cur ^ 1][row2] = w2;
-            if (row2 < lpi && state) {
-                st_stream(state + base + row2, v2);
-                if (BETA) st_stream(a.ctx.fcc_w + base + row2, w2);
-            }
-        }
-        if (!FULL && !has2 && cc == 0 && row2 < LP) sm.pvec[cur ^ 1][row2] = T(0);
-        if (!BETA && lane == 0) a.ctx.fcc_scale[(int64_t)n * tp + t] = sc;
-        last_w1 = w1; last_w2 = w2;
-        cur ^= 1;
+        T z1 = T(0);
+        if (FULL) z1 = E1.template dot<true>(pin);
+        T v1, v2, w1, w2;
+        if (BETA) { v1 = z1 * applied; v2 = z2 * applied; w1 = v1 * u1; w2 = v2 * u2; }
+        else { v1 = z1 * (u1 * applied); v2 = z2 * (u2 * applied); w1 = v1; w2 = v2; }
+        f1 = w1; f2 = w2;
+        publish(v1, v2, w1, w2, pout, applied);
         __syncwarp();
-        if (lane == 0) st_volatile_s32(&sm.consumed, k + 1);
+    };
+    int k = 1;
+    for (; k + 1 < Tn; k += 2) {
+        one_step(k, sm.pvec[1], sm.pvec[0]);
+        one_step(k + 1, sm.pvec[0], sm.pvec[1]);
     }
+    if (k < Tn) one_step(k, sm.pvec[1], sm.pvec[0]);
+    if (lane == 0) st_volatile_s32(&sm.consumed, Tn);
+
     // ---- score: log(sum of the final weighted state) + bookkeeping -----------------------------
-    if (Tn > 0) {
-        T tot = warp_sum((FULL ? last_w1 : T(0)) + ((has2 && cc == 0) ? last_w2 : T(0)));
-        const double msum = wait_msum(&sm.msum, &sm.msum_ready);
-        if (lane == 0) {
-            const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
-                                 (double)esum * 0.6931471805599453094;
-            a.ctx.scalars[(int64_t)n * 8 + (BETA ? SC_FULL_BETA : SC_FULL_ALPHA)] = score;
-            a.ctx.scalars[(int64_t)n * 8 + SC_R] = (double)R;
-            if (BETA && a.full_scores) a.full_scores[n] = (T)score;
-        }
-    } else if (lane == 0 && BETA && a.full_scores) {
-        a.full_scores[n] = T(0);
+    T tot = warp_sum((FULL ? f1 : T(0)) + ((has2 && cc == 0) ? f2 : T(0)));
+    const double msum = wait_msum(&sm.msum, &sm.msum_ready);
+    if (lane == 0) {
+        const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
+                             (double)esum * 0.6931471805599453094;
+        a.ctx.scalars[(int64_t)n * 8 + (BETA ? SC_FULL_BETA : SC_FULL_ALPHA)] = score;
+        a.ctx.scalars[(int64_t)n * 8 + SC_R] = (double)R;
+        if (BETA && a.full_scores) a.full_scores[n] = (T)score;
     }
 }
 
@@ -336,20 +387,30 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
     const int gl = warp * 32 + lane;            // global lane = block index
     const int s0 = gl * ASG_BLK;
     const bool owns = s0 < sp;
-    T *state = BETA ? a.fac_beta : a.fac_alpha;
-    int *estate = BETA ? a.ctx.fac_eb : a.ctx.fac_ea;
+    constexpr int KNB = 64;                     // a block never sits more than 2^KNB below the neighbour that feeds it
+
+    // state rows of this utterance are contiguous: walk them with pointers
+    const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
+    T *stp = BETA ? a.fac_beta : a.fac_alpha;
+    const bool store = owns && stp != nullptr;
+    int *esp = (BETA ? a.ctx.fac_eb : a.ctx.fac_ea) + row0 * nbp + gl;
+    if (stp) stp += row0 * sp + s0;
+    const int64_t sstep = BETA ? -(int64_t)sp : (int64_t)sp;
+    const int64_t estep = BETA ? -(int64_t)nbp : (int64_t)nbp;
+    const bool store_e = store && gl < nblk;
 
     T v[ASG_BLK];        // alpha: P ; beta: Q (mantissas)
     T w[ASG_BLK];        // beta only: emission-weighted state fed to the next step
     int Eme = 0;
     T mymax = T(0);      // max of what feeds the next step (alpha: v, beta: w)
-    int ready = 0;
     int cur = 0;
 
     for (int k = 0; k < Tn; ++k) {
         const int t = BETA ? (Tn - 1 - k) : k;
-        if (k >= ready) {
-            while ((ready = ld_volatile_s32(&sm.flags[0])) <= k) __nanosleep(20);
+        if ((k & (FB - 1)) == 0) {
+            if (lane == 0) st_volatile_s32(&sm.consumed[warp], k);   // frames < k are done with
+            const int need = min(k + FB, Tn);
+            while (ld_volatile_s32(&sm.flags[0]) < need) __nanosleep(20);
             __threadfence_block();
         }
         const T *urow = sm.uring + (size_t)(k % RING) * up;
@@ -377,34 +438,35 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
                 if (W > 1 && warp < W - 1) { nv = sm.xval[cur * (W + 1) + warp + 1]; ne = sm.xexp[cur * (W + 1) + warp + 1]; }
                 else { nv = T(0); ne = Eme; }
             }
-            if (mymax == T(0)) Eme = ne;                       // an empty block adopts its neighbour's exponent
-            nv *= Num<T>::exp2i(ne - Eme);
+            // Common exponent of this step.  An empty block adopts its neighbour's exponent; a block that sits far below
+            // the neighbour feeding it is pulled up (its own mantissas shrink by `fs`, harmlessly) so the inflow is
+            // always representable -- no clamping of real mass.
+            int Enew = Eme;
+            if (mymax == T(0)) Enew = ne;
+            else if (nv > T(0)) Enew = max(Eme, ne - KNB);
+            const T fs = Num<T>::exp2i(Eme - Enew);                // <= 1 (1 in the common case)
+            nv *= Num<T>::exp2i(ne - Enew);
+            Eme = Enew;
             T r[ASG_BLK];
             if (BETA) {
+                r[ASG_BLK - 1] = fma(h[ASG_BLK - 1], w[ASG_BLK - 1] * fs, dd[ASG_BLK - 1] * nv);
 #pragma unroll
-                for (int j = 0; j < ASG_BLK; ++j) {
-                    const T nxt = (j + 1 < ASG_BLK) ? w[(j + 1) % ASG_BLK] : nv;
-                    r[j] = fma(h[j], w[j], dd[j] * nxt);
-                }
+                for (int j = 0; j < ASG_BLK - 1; ++j) r[j] = fs * fma(h[j], w[j], dd[j] * w[j + 1]);
                 if (s0 + ASG_BLK - 1 > t) {                    // band: position s is reachable by frame t only if s <= t
 #pragma unroll
                     for (int j = 0; j < ASG_BLK; ++j) if (s0 + j > t) r[j] = T(0);
                 }
             } else {
+                r[0] = ub[0] * fma(h[0], v[0] * fs, dd[0] * nv);
 #pragma unroll
-                for (int j = 0; j < ASG_BLK; ++j) {
-                    const T prv = (j > 0) ? v[(j + ASG_BLK - 1) % ASG_BLK] : nv;
-                    r[j] = ub[j] * fma(h[j], v[j], dd[j] * prv);
-                }
+                for (int j = 1; j < ASG_BLK; ++j) r[j] = (ub[j] * fs) * fma(h[j], v[j], dd[j] * v[j - 1]);
                 const int lb = (Sn - 1) - (Tn - 1 - t);        // band: positions below lb can no longer finish
                 if (s0 < lb) {
 #pragma unroll
                     for (int j = 0; j < ASG_BLK; ++j) if (s0 + j < lb) r[j] = T(0);
                 }
             }
-            T m = r[0];
-#pragma unroll
-            for (int j = 1; j < ASG_BLK; ++j) m = tmax(m, r[j]);
+            const T m = tmax(tmax(tmax(r[0], r[1]), tmax(r[2], r[3])), tmax(tmax(r[4], r[5]), tmax(r[6], r[7])));
             T sc; int e;
             Num<T>::pow2_norm(m, sc, e);
 #pragma unroll
@@ -415,25 +477,26 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
         if (BETA) {
 #pragma unroll
             for (int j = 0; j < ASG_BLK; ++j) w[j] = v[j] * ub[j];
+            mymax = tmax(tmax(tmax(w[0], w[1]), tmax(w[2], w[3])), tmax(tmax(w[4], w[5]), tmax(w[6], w[7])));
+        } else {
+            mymax = tmax(tmax(tmax(v[0], v[1]), tmax(v[2], v[3])), tmax(tmax(v[4], v[5]), tmax(v[6], v[7])));
         }
-        mymax = BETA ? w[0] : v[0];
-#pragma unroll
-        for (int j = 1; j < ASG_BLK; ++j) mymax = tmax(mymax, BETA ? w[j] : v[j]);
 
         // store mantissas + exponent
-        if (owns && state) {
-            const int64_t row = (int64_t)n * tp + t;
-            store8_stream(state + row * sp + s0, v);
-            if (gl < nblk) estate[row * nbp + gl] = Eme;
+        if (store) {
+            store8_stream(stp, v);
+            if (store_e) *esp = Eme;
         }
+        stp += sstep;
+        esp += estep;
         if (W > 1) {
             if (!BETA && lane == 31) { sm.xval[(cur ^ 1) * (W + 1) + warp] = v[ASG_BLK - 1]; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
             if (BETA && lane == 0) { sm.xval[(cur ^ 1) * (W + 1) + warp] = w[0]; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
+            cur ^= 1;
+            named_bar_sync(1, 32 * W);
         }
-        cur ^= 1;
-        fac_consumer_sync(W);
-        if (lane == 0) st_volatile_s32(&sm.consumed[warp], k + 1);
     }
+    if (lane == 0) st_volatile_s32(&sm.consumed[warp], Tn);
     // ---- score ------------------------------------------------------------------------------------
     const double msum = (Tn > 0) ? wait_msum(sm.msum, &sm.flags[1]) : 0.0;
     if (gl == 0) {
