@@ -212,6 +212,9 @@ def run_b200(args):
         crit.transition.copy_(A.to(dev))
     last = {}
 
+    from torch_asg.sharded import FusedAllReduce
+    fused = FusedAllReduce(crit) if world > 1 else None
+
     def step(i):
         x = xs[i % nsets]
         if fwd_only:
@@ -219,7 +222,13 @@ def run_b200(args):
                 last["loss"] = crit(x, ys[i % nsets], il, tl)
             return
         x.grad = None
-        last["loss"] = sharded_asg_step(crit, x, ys[i % nsets], il, tl, global_batch=N * world)
+        if world == 1:                       # the plain public API: ASGLoss(...)(...) + backward()
+            crit.transition.grad = None
+            loss = crit(x, ys[i % nsets], il, tl)
+            loss.backward()
+            last["loss"] = loss.detach()
+        else:                                # + the one fused all-reduce of (gA, loss sum, count)
+            last["loss"] = sharded_asg_step(crit, x, ys[i % nsets], il, tl, global_batch=N * world, fused=fused)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -297,41 +306,60 @@ def run_b200(args):
                            "peak_source": peak_src}
 
     # ---- end to end through the C ABI with host buffers (rank-local, all ranks concurrently) ----------
+    # NCTX host contexts in flight (asg_host_submit / asg_host_wait): every step still copies its inputs from
+    # pinned host memory and its results (loss, grad_x, grad_A) back, but step i's H2D overlaps step i-1's
+    # kernels and step i-2's D2H.
+    NCTX = 3
     hx = xs[0].detach().cpu().pin_memory()
     hA = A.clone().pin_memory()
     hy = ys[0].cpu().pin_memory()
-    hloss = torch.empty(N).pin_memory()
-    hgx = torch.empty(T, N, L).pin_memory()
-    hgA = torch.empty(L, L).pin_memory()
-    h = ctypes.c_void_p()
+    outs = [(torch.empty(N).pin_memory(), torch.empty(T, N, L).pin_memory(), torch.empty(L, L).pin_memory()) for _ in range(NCTX)]
     i64 = ctypes.c_int64
-    rc = lib.asg_host_create(0, local, i64(T), i64(N), i64(L), i64(S), ctypes.byref(h))
-    assert rc == 0, lib.asg_last_error()
+    ctxs = []
+    for _ in range(NCTX):
+        h = ctypes.c_void_p()
+        rc = lib.asg_host_create(0, local, i64(T), i64(N), i64(L), i64(S), ctypes.byref(h))
+        assert rc == 0, lib.asg_last_error()
+        ctxs.append(h)
     vp = lambda tns: ctypes.c_void_p(tns.data_ptr())
 
-    def e2e_step():
-        rc = lib.asg_host_loss(h, vp(hx), vp(hA), vp(hy), None, None, None, i64(T), i64(N), i64(L), i64(S), vp(hloss),
-                               None if fwd_only else vp(hgx), None if fwd_only else vp(hgA))
+    def e2e_submit(j):
+        hloss, hgx, hgA = outs[j]
+        rc = lib.asg_host_submit(ctxs[j], vp(hx), vp(hA), vp(hy), None, None, None, i64(T), i64(N), i64(L), i64(S), vp(hloss),
+                                 None if fwd_only else vp(hgx), None if fwd_only else vp(hgA))
         assert rc == 0, lib.asg_last_error()
 
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
+    def e2e_wait(j):
+        rc = lib.asg_host_wait(ctxs[j])
+        assert rc == 0, lib.asg_last_error()
+
+    def e2e_run(nsteps):
+        for i in range(nsteps):
+            if i >= NCTX:
+                e2e_wait(i % NCTX)           # results of step i-NCTX are in host memory
+            e2e_submit(i % NCTX)
+        for j in range(min(NCTX, nsteps)):
+            e2e_wait(j)
+
+    e2e_run(max(3, args.warmup))
     sync_all()
     esteps = args.steps
     t0 = time.perf_counter()
-    for _ in range(esteps):
-        e2e_step()               # blocks until the results are in host memory
+    e2e_run(esteps)                          # returns when every step's results are in host memory
     dt = time.perf_counter() - t0
-    lib.asg_host_destroy(h)
+    e2e_loss = float(outs[0][0].mean())
+    for h in ctxs:
+        lib.asg_host_destroy(h)
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     h2d = hx.numel() * 4 + hA.numel() * 4 + hy.numel() * 8
-    d2h = N * 4 + (0 if fwd_only else (hgx.numel() * 4 + hgA.numel() * 4))
+    d2h = N * 4 + (0 if fwd_only else (outs[0][1].numel() * 4 + outs[0][2].numel() * 4))
     out["e2e"] = {"value": N * world * esteps / dt, "unit": "utterances/s", "h2d_bytes_per_step": h2d,
-                  "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / esteps,
-                  "api": "asg_host_loss (C ABI, pinned host buffers; loss + grad_x + grad_A copied back)"}
+                  "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / esteps, "loss": e2e_loss,
+                  "api": "asg_host_submit/asg_host_wait (C ABI, pinned host buffers, %d contexts in flight; every step copies "
+                         "x, A, y in and loss, grad_x, grad_A out)" % NCTX}
 
     # ---- the reference's CPU path on this box's host cores (rank 0, single-GPU run only) --------------
     if world == 1 and not args.no_cpu_baseline:

@@ -161,6 +161,18 @@ int asg_host_loss(asg_host_ctx_t *h,
                   const void *g, int64_t T, int64_t N, int64_t L, int64_t S,
                   void *loss, void *grad_x, void *grad_A);
 
+/*
+ * The same, split for pipelining: asg_host_submit() enqueues the copies and kernels on the context's private
+ * stream and returns; asg_host_wait() blocks until that context's results are in host memory.  Several contexts
+ * may be in flight at once (one submit per context between waits): the H2D of one step then overlaps the
+ * kernels of the previous one and the D2H of the one before.  Host buffers must be pinned for the overlap.
+ */
+int asg_host_submit(asg_host_ctx_t *h,
+                    const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
+                    const void *g, int64_t T, int64_t N, int64_t L, int64_t S,
+                    void *loss, void *grad_x, void *grad_A);
+int asg_host_wait(asg_host_ctx_t *h);
+
 const char *asg_last_error(void);
 const char *asg_version(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */

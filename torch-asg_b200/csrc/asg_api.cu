@@ -279,11 +279,11 @@ void asg_host_destroy(asg_host_ctx_t *h) {
     delete h;
 }
 
-int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
-                  const void *g, int64_t T, int64_t N, int64_t L, int64_t S, void *loss, void *grad_x, void *grad_A) {
-    if (!h || !x || !A || !y || !loss) return fail(ASG_E_NULL, "asg_host_loss: h, x, A, y, loss are required");
+int asg_host_submit(asg_host_ctx_t *h, const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
+                    const void *g, int64_t T, int64_t N, int64_t L, int64_t S, void *loss, void *grad_x, void *grad_A) {
+    if (!h || !x || !A || !y || !loss) return fail(ASG_E_NULL, "asg_host_submit: h, x, A, y, loss are required");
     if (T != h->T || N != h->N || L != h->L || S != h->S)
-        return fail(ASG_E_SHAPE, "asg_host_loss: shape differs from the one the context was created for");
+        return fail(ASG_E_SHAPE, "asg_host_submit: shape differs from the one the context was created for");
     int e = cudaSetDevice(h->device);
     if (e) return cuda_fail(e, "cudaSetDevice");
     const size_t eb = h->lay.elem_bytes;
@@ -318,9 +318,22 @@ int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t
         if (grad_x) ASG_TRY(cudaMemcpyAsync(grad_x, d + h->o_gx, eb * (size_t)T * N * L, cudaMemcpyDeviceToHost, st), "D2H grad_x");
         if (grad_A) ASG_TRY(cudaMemcpyAsync(grad_A, d + h->o_gA, eb * (size_t)L * L, cudaMemcpyDeviceToHost, st), "D2H grad_A");
     }
-    ASG_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
 #undef ASG_TRY
     return 0;
+}
+
+int asg_host_wait(asg_host_ctx_t *h) {
+    if (!h) return fail(ASG_E_NULL, "asg_host_wait: h is NULL");
+    int e = cudaSetDevice(h->device);
+    if (e) return cuda_fail(e, "cudaSetDevice");
+    return cuda_fail((int)cudaStreamSynchronize(h->stream), "cudaStreamSynchronize");
+}
+
+int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
+                  const void *g, int64_t T, int64_t N, int64_t L, int64_t S, void *loss, void *grad_x, void *grad_A) {
+    int rc = asg_host_submit(h, x, A, y, il, tl, g, T, N, L, S, loss, grad_x, grad_A);
+    if (rc) return rc;
+    return asg_host_wait(h);
 }
 
 const char *asg_last_error(void) { return g_err; }

@@ -524,6 +524,199 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// float specialisation of the FAC consumer: the same arithmetic as fac_consumer<float,...>, written for the issue
+// rate of a lone warp -- packed FMUL2/FFMA2 on position pairs (j, j+4) (the shifted neighbour pair of (j, j+4) is the
+// aligned pair (j-1, j+3)), 32-bit shared-memory addressing for the label gather, pointer-walked stores.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float max8(const float2 (&p)[4]) {
+    return fmaxf(fmaxf(fmaxf(p[0].x, p[0].y), fmaxf(p[1].x, p[1].y)), fmaxf(fmaxf(p[2].x, p[2].y), fmaxf(p[3].x, p[3].y)));
+}
+
+template <bool BETA>
+__device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &sm, int W, int n, int Tn, int Sn, float Rb,
+                                 const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
+    typedef float T;
+    const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp;
+    const int up = (int)a.ctx.lpi + 4;
+    const int64_t tp = a.ctx.tp;
+    const int gl = warp * 32 + lane;
+    const int s0 = gl * ASG_BLK;
+    const bool owns = s0 < sp;
+    constexpr int KNB = 64;
+
+    const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
+    T *stp = BETA ? a.fac_beta : a.fac_alpha;
+    const bool store = owns && stp != nullptr;
+    int *esp = (BETA ? a.ctx.fac_eb : a.ctx.fac_ea) + row0 * nbp + gl;
+    if (stp) stp += row0 * sp + s0;
+    const int64_t sstep = BETA ? -(int64_t)sp : (int64_t)sp;
+    const int64_t estep = BETA ? -(int64_t)nbp : (int64_t)nbp;
+    const bool store_e = store && gl < nblk;
+
+    // pairs: index q holds positions (q, q+4) of this lane's block
+    float2 h2[4], d2[4];
+    unsigned la[8];                                   // shared-memory byte address of u[lab[j]] in ring slot 0
+    const unsigned ring0 = smem_u32(sm.uring);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { h2[q] = make_float2(h[q], h[q + 4]); d2[q] = make_float2(dd[q], dd[q + 4]); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) la[j] = ring0 + 4u * (unsigned)lab[j];
+    const unsigned slot_bytes = 4u * (unsigned)up;
+
+    float2 P[4];         // alpha: state = feed; beta: state Q
+    float2 Wf[4];        // beta: feed = Q o u
+    int Eme = 0;
+    float mymax = 0.f;
+    int cur = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { P[q] = make_float2(0.f, 0.f); Wf[q] = P[q]; }
+
+    unsigned slot_off = 0;                            // byte offset of ring slot (k % RING)
+    for (int k = 0; k < Tn; ++k) {
+        const int t = BETA ? (Tn - 1 - k) : k;
+        if ((k & (FB - 1)) == 0) {
+            if (lane == 0) st_volatile_s32(&sm.consumed[warp], k);
+            const int need = min(k + FB, Tn);
+            while (ld_volatile_s32(&sm.flags[0]) < need) __nanosleep(20);
+            __threadfence_block();
+        }
+        float2 u2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { u2[q].x = lds_f32(la[q] + slot_off); u2[q].y = lds_f32(la[q + 4] + slot_off); }
+        slot_off = (k % RING == RING - 1) ? 0u : slot_off + slot_bytes;
+
+        if (k == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (BETA) { P[q].x = (s0 + q == Sn - 1) ? 1.f : 0.f; P[q].y = (s0 + q + 4 == Sn - 1) ? 1.f : 0.f; }
+                else { P[q].x = (s0 + q == 0) ? u2[q].x : 0.f; P[q].y = 0.f; }
+            }
+        } else {
+            // neighbour's boundary value and exponent from the previous step
+            float nv; int ne;
+            const float src = BETA ? Wf[0].x : P[3].y;            // beta: w[0]; alpha: v[7]
+            if (BETA) { nv = __shfl_down_sync(ASG_FULL_MASK, src, 1); ne = __shfl_down_sync(ASG_FULL_MASK, Eme, 1); }
+            else { nv = __shfl_up_sync(ASG_FULL_MASK, src, 1); ne = __shfl_up_sync(ASG_FULL_MASK, Eme, 1); }
+            if (!BETA && lane == 0) {
+                if (W > 1 && warp > 0) { nv = sm.xval[cur * (W + 1) + warp - 1]; ne = sm.xexp[cur * (W + 1) + warp - 1]; }
+                else { nv = 0.f; ne = Eme; }
+            }
+            if (BETA && lane == 31) {
+                if (W > 1 && warp < W - 1) { nv = sm.xval[cur * (W + 1) + warp + 1]; ne = sm.xexp[cur * (W + 1) + warp + 1]; }
+                else { nv = 0.f; ne = Eme; }
+            }
+            int Enew = Eme;
+            if (mymax == 0.f) Enew = ne;
+            else if (nv > 0.f) Enew = max(Eme, ne - KNB);
+            const float fs = Num<T>::exp2i(Eme - Enew);
+            nv *= Num<T>::exp2i(ne - Enew);
+            Eme = Enew;
+            const float2 fs2 = make_float2(fs, fs);
+            float2 r2[4];
+            if (BETA) {
+                // r[j] = fs * (h[j] w[j] + d[j] w[j+1]);  pair (j, j+4) needs (w[j+1], w[j+5]) = pair j+1; j = 3: (w[4], nv)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 nx = (q < 3) ? Wf[(q + 1) & 3] : make_float2(Wf[0].y, 0.f);
+                    r2[q] = __fmul2_rn(fs2, __ffma2_rn(h2[q], Wf[q], __fmul2_rn(d2[q], nx)));
+                }
+                r2[3].y = fmaf(h2[3].y, Wf[3].y * fs, d2[3].y * nv);
+                if (s0 + ASG_BLK - 1 > t) {                    // band: position s is reachable by frame t only if s <= t
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { if (s0 + q > t) r2[q].x = 0.f; if (s0 + q + 4 > t) r2[q].y = 0.f; }
+                }
+            } else {
+                // r[j] = (u[j] fs) * (h[j] v[j] + d[j] v[j-1]);  pair (j, j+4) needs (v[j-1], v[j+3]) = pair j-1; j = 0: (nv, v[3])
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 pv = (q > 0) ? P[(q + 3) & 3] : make_float2(0.f, P[3].x);
+                    r2[q] = __fmul2_rn(__fmul2_rn(u2[q], fs2), __ffma2_rn(h2[q], P[q], __fmul2_rn(d2[q], pv)));
+                }
+                r2[0].x = u2[0].x * fmaf(h2[0].x, P[0].x * fs, d2[0].x * nv);
+                const int lb = (Sn - 1) - (Tn - 1 - t);        // band: positions below lb can no longer finish
+                if (s0 < lb) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { if (s0 + q < lb) r2[q].x = 0.f; if (s0 + q + 4 < lb) r2[q].y = 0.f; }
+                }
+            }
+            const float m = max8(r2);
+            float sc; int e;
+            Num<T>::pow2_norm(m, sc, e);
+            const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) P[q] = __fmul2_rn(r2[q], sc2);
+            Eme += e;
+            mymax = m * sc;                                     // alpha: the feed is the state itself
+        }
+        if (BETA) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Wf[q] = __fmul2_rn(P[q], u2[q]);
+            mymax = max8(Wf);
+        } else if (k == 0) {
+            mymax = max8(P);
+        }
+
+        if (store) {
+            __stcs(reinterpret_cast<float4 *>(stp), make_float4(P[0].x, P[1].x, P[2].x, P[3].x));
+            __stcs(reinterpret_cast<float4 *>(stp) + 1, make_float4(P[0].y, P[1].y, P[2].y, P[3].y));
+            if (store_e) *esp = Eme;
+        }
+        stp += sstep;
+        esp += estep;
+        if (W > 1) {
+            if (!BETA && lane == 31) { sm.xval[(cur ^ 1) * (W + 1) + warp] = P[3].y; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
+            if (BETA && lane == 0) { sm.xval[(cur ^ 1) * (W + 1) + warp] = Wf[0].x; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
+            cur ^= 1;
+            named_bar_sync(1, 32 * W);
+        }
+    }
+    if (lane == 0) st_volatile_s32(&sm.consumed[warp], Tn);
+    // ---- score ------------------------------------------------------------------------------------
+    const double msum = (Tn > 0) ? wait_msum(sm.msum, &sm.flags[1]) : 0.0;
+    if (gl == 0) {
+        double score = 0.0;
+        if (Tn > 0) {
+            const T fin = BETA ? Wf[0].x : T(0);
+            score = (double)Num<T>::log_(fin) + msum + (double)(Tn - 1) * (double)Rb + (double)Eme * 0.6931471805599453094;
+        }
+        if (BETA) {
+            a.ctx.scalars[(int64_t)n * 8 + SC_AL_BETA] = score;
+            a.ctx.scalars[(int64_t)n * 8 + SC_RB] = (double)Rb;
+            if (a.aligned_scores) a.aligned_scores[n] = (T)score;
+        }
+    }
+    if (!BETA && Tn > 0) {      // alpha-side score (cross-check): mass at (T_n-1, S_n-1)
+        const int sl = Sn - 1;
+        if (sl >= s0 && sl < s0 + ASG_BLK) {
+            T fin = T(0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { if (s0 + q == sl) fin = P[q].x; if (s0 + q + 4 == sl) fin = P[q].y; }
+            a.ctx.scalars[(int64_t)n * 8 + SC_AL_ALPHA] =
+                (double)Num<T>::log_(fin) + msum + (double)(Tn - 1) * (double)Rb + (double)Eme * 0.6931471805599453094;
+        }
+    }
+}
+
+// dispatch: float -> packed specialisation, double -> generic
+template <typename T, bool BETA> struct FacConsumer {
+    __device__ static void run(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, int n, int Tn, int Sn, T Rb, const T (&h)[ASG_BLK],
+                               const T (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
+        fac_consumer<T, BETA>(a, sm, W, n, Tn, Sn, Rb, h, dd, lab, warp, lane);
+    }
+};
+template <bool BETA> struct FacConsumer<float, BETA> {
+    __device__ static void run(const ScanArgs<float> &a, FacSmemView<float> &sm, int W, int n, int Tn, int Sn, float Rb,
+                               const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
+        fac_consumer_f32<BETA>(a, sm, W, n, Tn, Sn, Rb, h, dd, lab, warp, lane);
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int W) {
     extern __shared__ __align__(16) char smem_raw[];
@@ -621,9 +814,9 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
         }
 #pragma unroll
         for (int j = 0; j < ASG_BLK; ++j) din[j] = (j == 0) ? left : dout[(j + ASG_BLK - 1) % ASG_BLK];
-        fac_consumer<T, false>(a, sm, W, n, Tn, Sn, Rb, h, din, lab, warp, lane);
+        FacConsumer<T, false>::run(a, sm, W, n, Tn, Sn, Rb, h, din, lab, warp, lane);
     } else {
-        fac_consumer<T, true>(a, sm, W, n, Tn, Sn, Rb, h, dout, lab, warp, lane);
+        FacConsumer<T, true>::run(a, sm, W, n, Tn, Sn, Rb, h, dout, lab, warp, lane);
     }
 }
 

@@ -50,8 +50,34 @@ def unpack_after_allreduce(buf, num_labels):
     return buf[:-2].view(num_labels, num_labels), buf[-2], buf[-1]
 
 
+class FusedAllReduce:
+    """Persistent fused buffer ``[L*L + 2]`` = (transition gradient, loss sum, utterance count).
+
+    ``criterion.transition.grad`` is made a VIEW of the buffer's head, so autograd accumulates the local
+    transition gradient straight into it and the single ``all_reduce`` needs no packing or unpacking copies.
+    """
+
+    def __init__(self, criterion, group=None):
+        p = criterion.transition
+        self.num_labels = p.shape[0]
+        self.buf = torch.zeros(p.numel() + 2, dtype=p.dtype, device=p.device)
+        self.grad_view = self.buf[:-2].view_as(p)
+        self.group = group
+
+    def prepare(self, criterion):
+        self.buf.zero_()
+        criterion.transition.grad = self.grad_view
+
+    def reduce(self, loss_sum, count):
+        self.buf[-2] = loss_sum
+        self.buf[-1] = count
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        return self.buf[-2], self.buf[-1]
+
+
 def sharded_asg_step(criterion, inputs, targets, input_lengths=None, target_lengths=None, group=None,
-                     global_batch=None):
+                     global_batch=None, fused=None):
     """One forward+backward of ``criterion`` (an ``ASGLoss`` whose ``reduction`` is honoured GLOBALLY) on
     this rank's utterances, followed by the single fused all-reduce.
 
@@ -59,29 +85,24 @@ def sharded_asg_step(criterion, inputs, targets, input_lengths=None, target_leng
     ``criterion.transition.grad`` holds the global transition gradient on every rank, ``inputs.grad`` the
     local input gradient (already scaled for the global reduction), and the returned scalar is the global
     reduced loss.  With ``reduction='mean'`` the upstream gradient is ``1/global_batch`` (not ``1/local``).
+    Pass a :class:`FusedAllReduce` as ``fused`` to reuse its buffer across steps.
     """
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     n_local = inputs.shape[1]
     if global_batch is None:
         global_batch = n_local * world
     reduction = criterion.reduction
-    saved = criterion.reduction
-    criterion.reduction = 'none'
+    if fused is None:
+        fused = FusedAllReduce(criterion, group)
+    fused.prepare(criterion)
+    criterion.reduction = 'sum'
     try:
-        per_utt = criterion(inputs, targets, input_lengths, target_lengths)
+        local_sum = criterion(inputs, targets, input_lengths, target_lengths)
     finally:
-        criterion.reduction = saved
-    local_sum = per_utt.sum()
+        criterion.reduction = reduction
     scale = 1.0 / global_batch if reduction == 'mean' else 1.0
-    if criterion.transition.grad is not None:
-        criterion.transition.grad = None
     (local_sum * scale).backward()
-    gA = criterion.transition.grad
-    buf = pack_for_allreduce(gA, local_sum.detach(), float(n_local))
-    if world > 1:
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    gA_glob, loss_sum, count = unpack_after_allreduce(buf, gA.shape[0])
-    criterion.transition.grad = gA_glob.clone()
+    loss_sum, count = fused.reduce(local_sum.detach(), float(n_local))
     if reduction == 'mean':
         return loss_sum / count
     return loss_sum
