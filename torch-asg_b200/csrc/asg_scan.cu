@@ -538,26 +538,37 @@ __device__ __forceinline__ float max8(const float2 (&p)[4]) {
     return fmaxf(fmaxf(fmaxf(p[0].x, p[0].y), fmaxf(p[1].x, p[1].y)), fmaxf(fmaxf(p[2].x, p[2].y), fmaxf(p[3].x, p[3].y)));
 }
 
+// exact power of two that brings m (>= 0, finite) into [1,2): scale = 2^-e.  m == 0 or denormal leaves the block alone.
+__device__ __forceinline__ void pow2_fast(float m, float &scale, int &e) {
+    const int eb = __float_as_int(m) >> 23;                // m >= 0: no sign bit
+    const bool live = eb != 0;
+    scale = live ? __int_as_float((254 - eb) << 23) : 1.0f;
+    e = live ? eb - 127 : 0;
+}
+
+// One consumer warp (S <= 256).  Lane boundaries need no special cases: shfl_up/down hand the edge lane its OWN
+// value, which a per-lane 0/1 mask turns into "no neighbour".  The boundary value travels UN-normalised, together
+// with the exponent it is expressed in, as soon as it exists -- the shuffle overlaps the normalisation of the step.
 template <bool BETA>
-__device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &sm, int W, int n, int Tn, int Sn, float Rb,
-                                 const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
+__device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &sm, int n, int Tn, int Sn, float Rb,
+                                 const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int lane) {
     typedef float T;
     const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp;
     const int up = (int)a.ctx.lpi + 4;
     const int64_t tp = a.ctx.tp;
-    const int gl = warp * 32 + lane;
-    const int s0 = gl * ASG_BLK;
+    const int s0 = lane * ASG_BLK;
     const bool owns = s0 < sp;
     constexpr int KNB = 64;
 
     const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
     T *stp = BETA ? a.fac_beta : a.fac_alpha;
     const bool store = owns && stp != nullptr;
-    int *esp = (BETA ? a.ctx.fac_eb : a.ctx.fac_ea) + row0 * nbp + gl;
+    int *esp = (BETA ? a.ctx.fac_eb : a.ctx.fac_ea) + row0 * nbp + lane;
     if (stp) stp += row0 * sp + s0;
     const int64_t sstep = BETA ? -(int64_t)sp : (int64_t)sp;
     const int64_t estep = BETA ? -(int64_t)nbp : (int64_t)nbp;
-    const bool store_e = store && gl < nblk;
+    const bool store_e = store && lane < nblk;
+    const float edge_mask = BETA ? (lane == 31 ? 0.f : 1.f) : (lane == 0 ? 0.f : 1.f);
 
     // pairs: index q holds positions (q, q+4) of this lane's block
     float2 h2[4], d2[4];
@@ -573,7 +584,8 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
     float2 Wf[4];        // beta: feed = Q o u
     int Eme = 0;
     float mymax = 0.f;
-    int cur = 0;
+    float nv = 0.f;      // neighbour's boundary value of the previous step, expressed in 2^ne
+    int ne = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) { P[q] = make_float2(0.f, 0.f); Wf[q] = P[q]; }
 
@@ -581,7 +593,7 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
     for (int k = 0; k < Tn; ++k) {
         const int t = BETA ? (Tn - 1 - k) : k;
         if ((k & (FB - 1)) == 0) {
-            if (lane == 0) st_volatile_s32(&sm.consumed[warp], k);
+            if (lane == 0) st_volatile_s32(&sm.consumed[0], k);
             const int need = min(k + FB, Tn);
             while (ld_volatile_s32(&sm.flags[0]) < need) __nanosleep(20);
             __threadfence_block();
@@ -589,34 +601,29 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
         float2 u2[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) { u2[q].x = lds_f32(la[q] + slot_off); u2[q].y = lds_f32(la[q + 4] + slot_off); }
-        slot_off = (k % RING == RING - 1) ? 0u : slot_off + slot_bytes;
+        slot_off = ((k & (RING - 1)) == RING - 1) ? 0u : slot_off + slot_bytes;
 
+        float snd;       // boundary value handed to the neighbour, expressed in 2^Esnd
+        int Esnd;
         if (k == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (BETA) { P[q].x = (s0 + q == Sn - 1) ? 1.f : 0.f; P[q].y = (s0 + q + 4 == Sn - 1) ? 1.f : 0.f; }
                 else { P[q].x = (s0 + q == 0) ? u2[q].x : 0.f; P[q].y = 0.f; }
             }
+            snd = BETA ? P[0].x * u2[0].x : P[3].y;
+            Esnd = 0;
+            nv = BETA ? __shfl_down_sync(ASG_FULL_MASK, snd, 1) : __shfl_up_sync(ASG_FULL_MASK, snd, 1);
+            ne = BETA ? __shfl_down_sync(ASG_FULL_MASK, Esnd, 1) : __shfl_up_sync(ASG_FULL_MASK, Esnd, 1);
+            nv *= edge_mask;
+            mymax = BETA ? 0.f : max8(P);
         } else {
-            // neighbour's boundary value and exponent from the previous step
-            float nv; int ne;
-            const float src = BETA ? Wf[0].x : P[3].y;            // beta: w[0]; alpha: v[7]
-            if (BETA) { nv = __shfl_down_sync(ASG_FULL_MASK, src, 1); ne = __shfl_down_sync(ASG_FULL_MASK, Eme, 1); }
-            else { nv = __shfl_up_sync(ASG_FULL_MASK, src, 1); ne = __shfl_up_sync(ASG_FULL_MASK, Eme, 1); }
-            if (!BETA && lane == 0) {
-                if (W > 1 && warp > 0) { nv = sm.xval[cur * (W + 1) + warp - 1]; ne = sm.xexp[cur * (W + 1) + warp - 1]; }
-                else { nv = 0.f; ne = Eme; }
-            }
-            if (BETA && lane == 31) {
-                if (W > 1 && warp < W - 1) { nv = sm.xval[cur * (W + 1) + warp + 1]; ne = sm.xexp[cur * (W + 1) + warp + 1]; }
-                else { nv = 0.f; ne = Eme; }
-            }
-            int Enew = Eme;
-            if (mymax == 0.f) Enew = ne;
-            else if (nv > 0.f) Enew = max(Eme, ne - KNB);
+            // Common exponent of this step.  An empty block adopts its neighbour's exponent; a block far below the
+            // neighbour feeding it is pulled up (own mantissas shrink by fs) so the inflow is always representable.
+            const int pulled = max(Eme, ne - KNB);
+            const int Enew = (mymax == 0.f) ? ne : ((nv > 0.f) ? pulled : Eme);
             const float fs = Num<T>::exp2i(Eme - Enew);
-            nv *= Num<T>::exp2i(ne - Enew);
-            Eme = Enew;
+            const float nva = nv * Num<T>::exp2i(ne - Enew);
             const float2 fs2 = make_float2(fs, fs);
             float2 r2[4];
             if (BETA) {
@@ -626,11 +633,12 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
                     const float2 nx = (q < 3) ? Wf[(q + 1) & 3] : make_float2(Wf[0].y, 0.f);
                     r2[q] = __fmul2_rn(fs2, __ffma2_rn(h2[q], Wf[q], __fmul2_rn(d2[q], nx)));
                 }
-                r2[3].y = fmaf(h2[3].y, Wf[3].y * fs, d2[3].y * nv);
-                if (s0 + ASG_BLK - 1 > t) {                    // band: position s is reachable by frame t only if s <= t
+                r2[3].y = fmaf(h2[3].y, Wf[3].y * fs, d2[3].y * nva);
+                if (t < sp) {                                  // band (uniform test): position s is reachable by frame t only if s <= t
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { if (s0 + q > t) r2[q].x = 0.f; if (s0 + q + 4 > t) r2[q].y = 0.f; }
+                    for (int q = 0; q < 4; ++q) { r2[q].x = (s0 + q > t) ? 0.f : r2[q].x; r2[q].y = (s0 + q + 4 > t) ? 0.f : r2[q].y; }
                 }
+                snd = r2[0].x;                                 // completed with u below
             } else {
                 // r[j] = (u[j] fs) * (h[j] v[j] + d[j] v[j-1]);  pair (j, j+4) needs (v[j-1], v[j+3]) = pair j-1; j = 0: (nv, v[3])
 #pragma unroll
@@ -638,28 +646,33 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
                     const float2 pv = (q > 0) ? P[(q + 3) & 3] : make_float2(0.f, P[3].x);
                     r2[q] = __fmul2_rn(__fmul2_rn(u2[q], fs2), __ffma2_rn(h2[q], P[q], __fmul2_rn(d2[q], pv)));
                 }
-                r2[0].x = u2[0].x * fmaf(h2[0].x, P[0].x * fs, d2[0].x * nv);
+                r2[0].x = u2[0].x * fmaf(h2[0].x, P[0].x * fs, d2[0].x * nva);
                 const int lb = (Sn - 1) - (Tn - 1 - t);        // band: positions below lb can no longer finish
-                if (s0 < lb) {
+                if (lb > 0) {                                  // uniform test
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { if (s0 + q < lb) r2[q].x = 0.f; if (s0 + q + 4 < lb) r2[q].y = 0.f; }
+                    for (int q = 0; q < 4; ++q) { r2[q].x = (s0 + q < lb) ? 0.f : r2[q].x; r2[q].y = (s0 + q + 4 < lb) ? 0.f : r2[q].y; }
                 }
+                snd = r2[3].y;
             }
+            // hand the boundary to the neighbour now (un-normalised, in 2^Enew): the shuffle overlaps the normalisation
+            if (BETA) snd *= u2[0].x;
+            Esnd = Enew;
+            nv = BETA ? __shfl_down_sync(ASG_FULL_MASK, snd, 1) : __shfl_up_sync(ASG_FULL_MASK, snd, 1);
+            ne = BETA ? __shfl_down_sync(ASG_FULL_MASK, Esnd, 1) : __shfl_up_sync(ASG_FULL_MASK, Esnd, 1);
+            nv *= edge_mask;
             const float m = max8(r2);
             float sc; int e;
-            Num<T>::pow2_norm(m, sc, e);
+            pow2_fast(m, sc, e);
             const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
             for (int q = 0; q < 4; ++q) P[q] = __fmul2_rn(r2[q], sc2);
-            Eme += e;
+            Eme = Enew + e;
             mymax = m * sc;                                     // alpha: the feed is the state itself
         }
         if (BETA) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) Wf[q] = __fmul2_rn(P[q], u2[q]);
             mymax = max8(Wf);
-        } else if (k == 0) {
-            mymax = max8(P);
         }
 
         if (store) {
@@ -669,17 +682,11 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
         }
         stp += sstep;
         esp += estep;
-        if (W > 1) {
-            if (!BETA && lane == 31) { sm.xval[(cur ^ 1) * (W + 1) + warp] = P[3].y; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
-            if (BETA && lane == 0) { sm.xval[(cur ^ 1) * (W + 1) + warp] = Wf[0].x; sm.xexp[(cur ^ 1) * (W + 1) + warp] = Eme; }
-            cur ^= 1;
-            named_bar_sync(1, 32 * W);
-        }
     }
-    if (lane == 0) st_volatile_s32(&sm.consumed[warp], Tn);
+    if (lane == 0) st_volatile_s32(&sm.consumed[0], Tn);
     // ---- score ------------------------------------------------------------------------------------
     const double msum = (Tn > 0) ? wait_msum(sm.msum, &sm.flags[1]) : 0.0;
-    if (gl == 0) {
+    if (lane == 0) {
         double score = 0.0;
         if (Tn > 0) {
             const T fin = BETA ? Wf[0].x : T(0);
@@ -713,7 +720,8 @@ template <typename T, bool BETA> struct FacConsumer {
 template <bool BETA> struct FacConsumer<float, BETA> {
     __device__ static void run(const ScanArgs<float> &a, FacSmemView<float> &sm, int W, int n, int Tn, int Sn, float Rb,
                                const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
-        fac_consumer_f32<BETA>(a, sm, W, n, Tn, Sn, Rb, h, dd, lab, warp, lane);
+        if (W == 1) fac_consumer_f32<BETA>(a, sm, n, Tn, Sn, Rb, h, dd, lab, lane);
+        else fac_consumer<float, BETA>(a, sm, W, n, Tn, Sn, Rb, h, dd, lab, warp, lane);
     }
 };
 
