@@ -123,8 +123,32 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// shared -> global bulk copy (TMA store), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// waits until at most N of this thread's bulk groups are still READING their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // orders this thread's generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// shared-memory loads through 32-bit shared addresses (no generic->shared conversion in hot loops)
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// exact power of two that brings m (>= 0, finite) into [1,2): scale = 2^-e.  m == 0 or denormal leaves the block alone.
+__device__ __forceinline__ void pow2_fast(float m, float &scale, int &e) {
+    const int eb = __float_as_int(m) >> 23;                // m >= 0: no sign bit
+    const bool live = eb != 0;
+    scale = live ? __int_as_float((254 - eb) << 23) : 1.0f;
+    e = live ? eb - 127 : 0;
+}
 
 // volatile shared-memory progress counters (producer/consumer rings)
 __device__ __forceinline__ int ld_volatile_s32(const int *p) {

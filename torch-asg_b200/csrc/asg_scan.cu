@@ -36,10 +36,10 @@ constexpr int RING = NRAW * FB;   // depth of the u ring, in frames
 //   uring [RING][up]       u_t = exp(x_t - m_t); entries l >= L of a row are 0
 //   consumed_min()         frames every consumer has finished with
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool BETA, typename ConsumedFn>
+template <typename T, bool BETA, typename ConsumedFn, typename FlushFn>
 __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int rp, T *uring, int up, int *produced,
-                                              double *msum_out, int *msum_ready, ConsumedFn consumed_min, int n, int Tn,
-                                              int lane) {
+                                              double *msum_out, int *msum_ready, ConsumedFn consumed_min, FlushFn flush,
+                                              int ngroups, int n, int Tn, int lane) {
     const int L = a.d.L;
     const int f = lane >> 2, sub = lane & 3;
     const T *xn = a.x + (int64_t)n * a.x_sn;
@@ -59,38 +59,55 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
         cp_async_commit();
     }
     double msum = 0.0;
-    for (int b = 0; b < nb; ++b) {
-        cp_async_wait<NRAW - 1>();
-        const int k = b * FB + f;
-        const bool valid = k < Tn;
-        const T *src = raw + ((size_t)(b % NRAW) * FB + f) * rp;
-        T m = ninf;
-        if (valid)
-            for (int l = sub; l < L; l += 4) m = tmax(m, src[l]);
-        m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 1));
-        m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 2));
-        if (!(m > ninf)) m = T(0);                     // an all -inf frame
+    int b = 0, g = 0;       // next batch to produce, next group of finished state rows to flush
+    while (b < nb || g < ngroups) {
+        const int c = consumed_min();
+        bool progressed = false;
+        if (g < ngroups && c >= min((g + 1) * FB, Tn)) {         // the consumer has finished frames of group g
+            flush(g);
+            ++g;
+            progressed = true;
+        }
         const int hi = min((b + 1) * FB, Tn);
-        if (hi > RING) {                               // the slots of this batch must have been released
-            while (consumed_min() < hi - RING) __nanosleep(32);
-        }
-        T *dst = uring + (size_t)(k % RING) * up;
-        if (valid)                                     // (slots of frames >= Tn belong to frames not yet consumed)
-            for (int l = sub; l < up; l += 4) dst[l] = (l < L) ? Num<T>::exp_(src[l] - m) : T(0);
-        if (valid && sub == 0) msum += (double)m;
-        if (b + NRAW < nb) issue(b + NRAW);            // each lane re-fills only elements it has consumed itself
-        cp_async_commit();
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            st_volatile_s32(produced, hi);
-        }
-    }
-    cp_async_wait<0>();
+        if (b < nb && hi - RING <= c) {                          // the ring slots of batch b have been released
+            cp_async_wait<NRAW - 1>();
+            const int k = b * FB + f;
+            const bool valid = k < Tn;
+            const T *src = raw + ((size_t)(b % NRAW) * FB + f) * rp;
+            T m = ninf;
+            if (valid)
+                for (int l = sub; l < L; l += 4) m = tmax(m, src[l]);
+            m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 1));
+            m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 2));
+            if (!(m > ninf)) m = T(0);                     // an all -inf frame
+            T *dst = uring + (size_t)(k % RING) * up;
+            if (valid)                                     // (slots of frames >= Tn belong to frames not yet consumed)
+                for (int l = sub; l < up; l += 4) dst[l] = (l < L) ? Num<T>::exp_(src[l] - m) : T(0);
+            if (valid && sub == 0) msum += (double)m;
+            if (b + NRAW < nb) issue(b + NRAW);            // each lane re-fills only elements it has consumed itself
+            cp_async_commit();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                st_volatile_s32(produced, hi);
+            }
+            ++b;
+            progressed = true;
+            if (b == nb) {                                 // all frames published: hand over the sum of the maxima
+                cp_async_wait<0>();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(ASG_FULL_MASK, msum, o);
-    if (lane == 0) {
-        *msum_out = msum;
+                for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(ASG_FULL_MASK, msum, o);
+                if (lane == 0) {
+                    *msum_out = msum;
+                    __threadfence_block();
+                    st_volatile_s32(msum_ready, 1);
+                }
+            }
+        }
+        if (!progressed) __nanosleep(32);
+    }
+    if (nb == 0 && lane == 0) {
+        *msum_out = 0.0;
         __threadfence_block();
         st_volatile_s32(msum_ready, 1);
     }
@@ -105,17 +122,6 @@ __device__ __forceinline__ double wait_msum(const double *msum, const int *msum_
 // =============================================================================================
 // FCC
 // =============================================================================================
-template <typename T, int LP>
-struct FccSmem {
-    alignas(16) T raw[NRAW * FB * LP];
-    alignas(16) T uring[RING * LP];
-    alignas(16) T pvec[2][LP];
-    double msum;
-    int msum_ready;
-    int produced;
-    int consumed;
-};
-
 template <typename T>
 __device__ __forceinline__ T ehat_of(const T *A, int64_t s0, int64_t s1, int i, int j, int L, T R) {
     if (i >= L || j >= L) return T(0);
@@ -176,6 +182,29 @@ template <int NE> struct RowRegs<double, NE> {
     }
 };
 
+constexpr int PR = 32;            // FCC state ring, frames (4 groups of FB): finished rows leave by bulk (TMA) stores
+constexpr int PRG = PR / FB;
+
+template <typename T, int LP>
+struct FccSmem {
+    alignas(128) T raw[NRAW * FB * LP];
+    alignas(128) T uring[RING * LP];
+    alignas(128) T pring[PR * LP];     // the vector that feeds the next step: alpha P (= the state), beta u o Q
+    alignas(128) T qring[PR * LP];     // beta: the state Q
+    alignas(16) T scring[PR];          // alpha: power of two applied at each frame
+    double msum;
+    int msum_ready;
+    int produced;
+    int consumed;
+    int flushed;                       // groups whose shared-memory rows may be overwritten
+};
+
+// ring slot of step k.  beta walks frames backwards: inside a group the slots are reversed so that a group is a
+// run of ascending frames, i.e. ONE contiguous chunk of the utterance-major state arrays.
+template <bool BETA> __device__ __forceinline__ int pslot(int k) {
+    return BETA ? ((k & (PR - 1)) ^ (FB - 1)) : (k & (PR - 1));
+}
+
 template <typename T, int LP, bool BETA>
 __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) {
     constexpr bool FULL = (LP >= 32);
@@ -185,8 +214,6 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
     constexpr int CL = LP / CH;                                   // columns per chunk (even)
     constexpr int RBASE = FULL ? 32 : 0;
     const int L = a.d.L;
-    const int lpi = (int)a.ctx.lpi;
-    const int64_t tp = a.ctx.tp;
     const int rr = lane % RP, cc = lane / RP;
     const int row2 = RBASE + rr;
     const bool has2 = (REM > 0) && (rr < REM);
@@ -217,46 +244,39 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
         if (lane == 0 && BETA && a.full_scores) a.full_scores[n] = T(0);
         return;
     }
-
-    // state rows of this utterance are contiguous: walk them with pointers (forwards for alpha, backwards for beta)
-    const int64_t step = BETA ? -(int64_t)lpi : (int64_t)lpi;
-    const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
-    T *st1 = (BETA ? a.fcc_beta : a.fcc_alpha);
-    const bool store = st1 != nullptr;
-    T *stw = BETA ? a.ctx.fcc_w : nullptr;
-    T *scp = a.ctx.fcc_scale + row0;
-    const bool wr1 = FULL && lane < lpi, wr2 = has2 && cc == 0 && row2 < lpi;
-    const int o1 = lane, o2 = row2;
-    if (store) { st1 += row0 * lpi; if (BETA) stw += row0 * lpi; }
+    for (int l = lane; l < PR * LP; l += 32) { sm.pring[l] = T(0); if (BETA) sm.qring[l] = T(0); }
+    __syncwarp();
 
     int esum = 0;
     T sc = T(1);                // power of two applied at the NEXT step (from the maximum of the vector that feeds it)
     int e_next = 0;
-    T f1 = T(0), f2 = T(0);     // this lane's rows of the vector that feeds the next mat-vec (alpha: P, beta: u o Q)
+    T f1 = T(0), f2 = T(0);     // this lane's rows of the feeding vector
+    const bool wlo = has2 && cc == 0;
 
-    auto wait_batch = [&](int k) {      // frames k .. k+FB-1 (or up to Tn) must be in the ring
+    // group bookkeeping at k % FB == 0: frames < k are finished (their u slots may be refilled, their state rows may
+    // leave); frames k .. k+FB-1 must be in the u ring; the state slots about to be overwritten must have left.
+    auto group_sync = [&](int k) {
+        fence_proxy_async();                                    // this lane's ring writes -> visible to the bulk stores
+        __syncwarp();
+        if (lane == 0) st_volatile_s32(&sm.consumed, k);
         const int need = min(k + FB, Tn);
         while (ld_volatile_s32(&sm.produced) < need) __nanosleep(20);
+        const int gneed = k / FB - PRG + 1;
+        while (ld_volatile_s32(&sm.flushed) < gneed) __nanosleep(20);
         __threadfence_block();
     };
-    auto publish = [&](T v1, T v2, T w1, T w2, T *pout, T applied) {
-        if (FULL) pout[lane] = BETA ? w1 : v1;
-        if (has2 && cc == 0) pout[row2] = BETA ? w2 : v2;
-        if (store) {
-            if (wr1) { st_stream(st1 + o1, v1); if (BETA) st_stream(stw + o1, w1); }
-            if (wr2) { st_stream(st1 + o2, v2); if (BETA) st_stream(stw + o2, w2); }
-            st1 += step;
-            if (BETA) stw += step;
-        }
-        if (!BETA) { if (lane == 0) *scp = applied; scp += 1; }
+    auto publish = [&](int k, T v1, T v2, T w1, T w2, T applied) {
+        const int slot = pslot<BETA>(k) * LP;
+        if (FULL) { sm.pring[slot + lane] = BETA ? w1 : v1; if (BETA) sm.qring[slot + lane] = v1; }
+        if (wlo) { sm.pring[slot + row2] = BETA ? w2 : v2; if (BETA) sm.qring[slot + row2] = v2; }
+        if (!BETA && lane == 0) sm.scring[pslot<BETA>(k)] = applied;
         // the next step's scale: exact power of two from one REDUX over the feeding vector (off the dependent chain)
         const T M = Num<T>::warp_max_nonneg(tmax(BETA ? w1 : v1, BETA ? w2 : v2));
         Num<T>::pow2_norm(M, sc, e_next);
     };
 
     // ---- frame 0 --------------------------------------------------------------------------------
-    wait_batch(0);
-    if (!FULL) { for (int l = lane; l < LP; l += 32) { sm.pvec[0][l] = T(0); sm.pvec[1][l] = T(0); } __syncwarp(); }
+    group_sync(0);
     {
         const T *urow = sm.uring;
         const T u1 = FULL ? urow[lane] : T(0);
@@ -265,18 +285,16 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
         if (BETA) { v1 = (FULL && lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
         else { v1 = u1; v2 = u2; }
         f1 = BETA ? v1 * u1 : v1; f2 = BETA ? v2 * u2 : v2;
-        publish(v1, v2, f1, f2, sm.pvec[1], T(1));
+        publish(0, v1, v2, f1, f2, T(1));
         __syncwarp();
     }
     // ---- frames 1 .. Tn-1 -------------------------------------------------------------------------
-    auto one_step = [&](int k, const T *pin, T *pout) {
-        if ((k & (FB - 1)) == 0) {
-            if (lane == 0) st_volatile_s32(&sm.consumed, k);      // frames < k are done: their ring slots may be refilled
-            wait_batch(k);
-        }
-        const T *urow = sm.uring + (size_t)(k % RING) * LP;
+    for (int k = 1; k < Tn; ++k) {
+        if ((k & (FB - 1)) == 0) group_sync(k);
+        const T *urow = sm.uring + (k & (RING - 1)) * LP;
         const T u1 = FULL ? urow[lane] : T(0);
         const T u2 = has2 ? urow[row2] : T(0);
+        const T *pin = sm.pring + pslot<BETA>(k - 1) * LP;
         const T applied = sc;
         esum += e_next;
         T z2 = T(0);
@@ -291,19 +309,15 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
         if (BETA) { v1 = z1 * applied; v2 = z2 * applied; w1 = v1 * u1; w2 = v2 * u2; }
         else { v1 = z1 * (u1 * applied); v2 = z2 * (u2 * applied); w1 = v1; w2 = v2; }
         f1 = w1; f2 = w2;
-        publish(v1, v2, w1, w2, pout, applied);
+        publish(k, v1, v2, w1, w2, applied);
         __syncwarp();
-    };
-    int k = 1;
-    for (; k + 1 < Tn; k += 2) {
-        one_step(k, sm.pvec[1], sm.pvec[0]);
-        one_step(k + 1, sm.pvec[0], sm.pvec[1]);
     }
-    if (k < Tn) one_step(k, sm.pvec[1], sm.pvec[0]);
+    fence_proxy_async();
+    __syncwarp();
     if (lane == 0) st_volatile_s32(&sm.consumed, Tn);
 
     // ---- score: log(sum of the final weighted state) + bookkeeping -----------------------------
-    T tot = warp_sum((FULL ? f1 : T(0)) + ((has2 && cc == 0) ? f2 : T(0)));
+    T tot = warp_sum((FULL ? f1 : T(0)) + (wlo ? f2 : T(0)));
     const double msum = wait_msum(&sm.msum, &sm.msum_ready);
     if (lane == 0) {
         const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
@@ -314,23 +328,228 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// float specialisation of the FCC consumer: same arithmetic as fcc_consumer<float,...>, written for a lone warp --
+// all shared-memory traffic through 32-bit shared addresses (no per-step generic->shared conversion), the whole state
+// vector loaded up front (the loads' latency overlaps instead of being paid once per FFMA2), packed FFMA2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds_v4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_v2(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
+
+template <int LP, bool BETA>
+__device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &sm, int n, int Tn, int lane) {
+    typedef float T;
+    static_assert(LP >= 32, "the packed path covers LP >= 32");
+    constexpr int REM = LP - 32;                                  // rows handled with a column split
+    constexpr int RP = REM <= 8 ? 8 : (REM <= 16 ? 16 : 32);
+    constexpr int CH = 32 / RP;                                   // column chunks
+    constexpr int CL = LP / CH;                                   // columns per chunk (even)
+    const int L = a.d.L;
+    const int rr = lane % RP, cc = lane / RP;
+    const int row2 = 32 + rr;
+    const bool has2 = (REM > 0) && (rr < REM);
+
+    const T R = transition_max(a.A, a.A_s0, a.A_s1, L, lane);
+    float2 E1[LP / 2];
+    float2 E2[REM > 0 ? CL / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < LP / 2; ++j) {
+        E1[j].x = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, 2 * j, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, 2 * j, L, R);
+        E1[j].y = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, 2 * j + 1, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, 2 * j + 1, L, R);
+    }
+    if (REM > 0) {
+#pragma unroll
+        for (int c = 0; c < CL / 2; ++c) {
+            const int j = cc * CL + 2 * c;
+            E2[c].x = !has2 ? 0.f : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j, L, R));
+            E2[c].y = !has2 ? 0.f : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j + 1, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j + 1, L, R));
+        }
+    }
+    if (!BETA && n == 0) {   // publish E for the gradient assembly
+        for (int e = lane; e < L * L; e += 32) a.ctx.ehat[e] = ehat_of(a.A, a.A_s0, a.A_s1, e / L, e % L, L, R);
+    }
+    if (!BETA && lane == 0) a.ctx.il[n] = Tn;
+    if (Tn <= 0) {
+        if (lane == 0 && BETA && a.full_scores) a.full_scores[n] = T(0);
+        return;
+    }
+    for (int l = lane; l < PR * LP; l += 32) { sm.pring[l] = T(0); if (BETA) sm.qring[l] = T(0); }
+    __syncwarp();
+
+    // 32-bit shared addresses
+    const unsigned pr0 = smem_u32(sm.pring), qr0 = smem_u32(sm.qring), sc0 = smem_u32(sm.scring), ur0 = smem_u32(sm.uring);
+    constexpr unsigned ROWB = 4u * LP;
+    const unsigned l1 = 4u * (unsigned)lane, l2 = 4u * (unsigned)row2, ctail = 4u * (unsigned)(cc * CL);
+    const bool wlo = has2 && cc == 0;
+
+    int esum = 0;
+    T sc = T(1);
+    int e_next = 0;
+    T f1 = T(0), f2 = T(0);
+
+    auto group_sync = [&](int k) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) st_volatile_s32(&sm.consumed, k);
+        const int need = min(k + FB, Tn);
+        while (ld_volatile_s32(&sm.produced) < need) __nanosleep(20);
+        const int gneed = k / FB - PRG + 1;
+        while (ld_volatile_s32(&sm.flushed) < gneed) __nanosleep(20);
+        __threadfence_block();
+    };
+    auto publish = [&](int k, T v1, T v2, T w1, T w2, T applied) {
+        const unsigned slot = (unsigned)pslot<BETA>(k);
+        const unsigned rowoff = slot * ROWB;
+        sts_f32(pr0 + rowoff + l1, BETA ? w1 : v1);
+        if (BETA) sts_f32(qr0 + rowoff + l1, v1);
+        if (wlo) { sts_f32(pr0 + rowoff + l2, BETA ? w2 : v2); if (BETA) sts_f32(qr0 + rowoff + l2, v2); }
+        if (!BETA && lane == 0) sts_f32(sc0 + 4u * slot, applied);
+        const T M = Num<T>::warp_max_nonneg(fmaxf(BETA ? w1 : v1, BETA ? w2 : v2));
+        pow2_fast(M, sc, e_next);
+    };
+
+    // ---- frame 0 --------------------------------------------------------------------------------
+    group_sync(0);
+    {
+        const T u1 = lds_f32(ur0 + l1);
+        const T u2 = has2 ? lds_f32(ur0 + l2) : T(0);
+        T v1, v2;
+        if (BETA) { v1 = (lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
+        else { v1 = u1; v2 = u2; }
+        f1 = BETA ? v1 * u1 : v1; f2 = BETA ? v2 * u2 : v2;
+        publish(0, v1, v2, f1, f2, T(1));
+        __syncwarp();
+    }
+    // ---- frames 1 .. Tn-1 -------------------------------------------------------------------------
+    for (int k = 1; k < Tn; ++k) {
+        if ((k & (FB - 1)) == 0) group_sync(k);
+        const unsigned urow = ur0 + (unsigned)(k & (RING - 1)) * ROWB;
+        const unsigned pin = pr0 + (unsigned)pslot<BETA>(k - 1) * ROWB;
+        // the whole feeding vector first: 10 broadcast LDS.128 (+ the tail chunk), then nothing but FFMA2
+        float4 q[LP / 4];
+#pragma unroll
+        for (int i = 0; i < LP / 4; ++i) q[i] = lds_v4(pin + 16u * i);
+        float2 qt[REM > 0 ? CL / 2 : 1];
+        if (REM > 0) {
+#pragma unroll
+            for (int c = 0; c < CL / 2; ++c) qt[c] = lds_v2(pin + ctail + 8u * c);
+        }
+        const T u1 = lds_f32(urow + l1);
+        const T u2 = has2 ? lds_f32(urow + l2) : T(0);
+        const T applied = sc;
+        esum += e_next;
+        T z2 = T(0);
+        if (REM > 0) {
+            float2 t0 = make_float2(0.f, 0.f), t1 = t0;
+#pragma unroll
+            for (int c = 0; c < CL / 2; ++c) { if (c & 1) t1 = __ffma2_rn(E2[c], qt[c], t1); else t0 = __ffma2_rn(E2[c], qt[c], t0); }
+            t0 = __fadd2_rn(t0, t1);
+            z2 = t0.x + t0.y;
+#pragma unroll
+            for (int o = RP; o < 32; o <<= 1) z2 += __shfl_xor_sync(ASG_FULL_MASK, z2, o);
+        }
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int i = 0; i < LP / 4; ++i) {
+            if (i & 1) { a2 = __ffma2_rn(E1[2 * i], make_float2(q[i].x, q[i].y), a2); a3 = __ffma2_rn(E1[2 * i + 1], make_float2(q[i].z, q[i].w), a3); }
+            else { a0 = __ffma2_rn(E1[2 * i], make_float2(q[i].x, q[i].y), a0); a1 = __ffma2_rn(E1[2 * i + 1], make_float2(q[i].z, q[i].w), a1); }
+        }
+        a0 = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
+        const T z1 = a0.x + a0.y;
+        T v1, v2, w1, w2;
+        if (BETA) { v1 = z1 * applied; v2 = z2 * applied; w1 = v1 * u1; w2 = v2 * u2; }
+        else { v1 = z1 * (u1 * applied); v2 = z2 * (u2 * applied); w1 = v1; w2 = v2; }
+        f1 = w1; f2 = w2;
+        publish(k, v1, v2, w1, w2, applied);
+        __syncwarp();
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) st_volatile_s32(&sm.consumed, Tn);
+
+    T tot = warp_sum(f1 + (wlo ? f2 : T(0)));
+    const double msum = wait_msum(&sm.msum, &sm.msum_ready);
+    if (lane == 0) {
+        const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
+                             (double)esum * 0.6931471805599453094;
+        a.ctx.scalars[(int64_t)n * 8 + (BETA ? SC_FULL_BETA : SC_FULL_ALPHA)] = score;
+        a.ctx.scalars[(int64_t)n * 8 + SC_R] = (double)R;
+        if (BETA && a.full_scores) a.full_scores[n] = (T)score;
+    }
+}
+
+// dispatch: float with LP >= 32 -> packed specialisation, everything else -> generic
+template <typename T, int LP, bool BETA> struct FccConsumer {
+    __device__ static void run(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) { fcc_consumer<T, LP, BETA>(a, sm, n, Tn, lane); }
+};
+template <int LP, bool BETA> struct FccConsumer<float, LP, BETA> {
+    __device__ static void run(const ScanArgs<float> &a, FccSmem<float, LP> &sm, int n, int Tn, int lane) {
+        if constexpr (LP >= 32) fcc_consumer_f32<LP, BETA>(a, sm, n, Tn, lane);
+        else fcc_consumer<float, LP, BETA>(a, sm, n, Tn, lane);
+    }
+};
+
+// producer-side: group g of finished state rows -> global memory, with bulk (TMA) stores
+template <typename T, int LP, bool BETA>
+__device__ __forceinline__ void fcc_flush_group(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int g, int lane) {
+    const int lpi = (int)a.ctx.lpi;
+    const int rows = min(FB, Tn - g * FB);
+    T *st = BETA ? a.fcc_beta : a.fcc_alpha;
+    if (lane == 0) {
+        if (st != nullptr) {
+            const int s0 = (g % PRG) * FB + (BETA ? FB - rows : 0);           // first ring slot of the run (ascending frames)
+            const int t0 = BETA ? (Tn - g * FB - rows) : g * FB;                // first frame of the run
+            const int64_t grow = (int64_t)n * a.ctx.tp + t0;
+            const T *feed = sm.pring + s0 * LP, *stat = sm.qring + s0 * LP;
+            T *dst_feed = BETA ? a.ctx.fcc_w : st;                               // beta: the feed ring is u o Q, qring the state
+            if (LP == lpi) {
+                bulk_s2g(dst_feed + grow * lpi, feed, (unsigned)(sizeof(T) * rows * lpi));
+                if (BETA) bulk_s2g(st + grow * lpi, stat, (unsigned)(sizeof(T) * rows * lpi));
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    bulk_s2g(dst_feed + (grow + r) * lpi, feed + r * LP, (unsigned)(sizeof(T) * lpi));
+                    if (BETA) bulk_s2g(st + (grow + r) * lpi, stat + r * LP, (unsigned)(sizeof(T) * lpi));
+                }
+            }
+            if (!BETA) bulk_s2g(a.ctx.fcc_scale + grow, sm.scring + s0, (unsigned)(sizeof(T) * ((rows + 3) / 4 * 4)));
+        }
+        bulk_commit();
+        // all but the newest group have been read out of shared memory: their slots are free again
+        if (g * FB + rows >= Tn) { bulk_wait_all<0>(); st_volatile_s32(&sm.flushed, g + 1); }
+        else { bulk_wait_read<1>(); st_volatile_s32(&sm.flushed, g); }
+    }
+}
+
 template <typename T, int LP>
-__global__ void __launch_bounds__(64) fcc_scan_kernel(const ScanArgs<T> a) {
-    __shared__ FccSmem<T, LP> sm;
+__global__ void __launch_bounds__(64, 1) fcc_scan_kernel(const ScanArgs<T> a) {
+    extern __shared__ __align__(128) char fcc_smem_raw[];
+    FccSmem<T, LP> &sm = *reinterpret_cast<FccSmem<T, LP> *>(fcc_smem_raw);
     const int n = blockIdx.x;
     const int dir = blockIdx.y == 0 ? a.dir0 : a.dir1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { sm.produced = 0; sm.consumed = 0; sm.msum_ready = 0; }
+    if (threadIdx.x == 0) { sm.produced = 0; sm.consumed = 0; sm.msum_ready = 0; sm.flushed = 0; }
     __syncthreads();
     int Tn = a.il ? (int)a.il[n] : a.d.T;
     Tn = max(0, min(Tn, a.d.T));
     auto cons = [&]() { return ld_volatile_s32(&sm.consumed); };
+    const int ngroups = (Tn + FB - 1) / FB;
     if (dir == 0) {
-        if (warp == 0) fcc_consumer<T, LP, false>(a, sm, n, Tn, lane);
-        else scan_producer<T, false>(a, sm.raw, LP, sm.uring, LP, &sm.produced, &sm.msum, &sm.msum_ready, cons, n, Tn, lane);
+        if (warp == 0) FccConsumer<T, LP, false>::run(a, sm, n, Tn, lane);
+        else scan_producer<T, false>(a, sm.raw, LP, sm.uring, LP, &sm.produced, &sm.msum, &sm.msum_ready, cons,
+                                     [&](int g) { fcc_flush_group<T, LP, false>(a, sm, n, Tn, g, lane); }, ngroups, n, Tn, lane);
     } else {
-        if (warp == 0) fcc_consumer<T, LP, true>(a, sm, n, Tn, lane);
-        else scan_producer<T, true>(a, sm.raw, LP, sm.uring, LP, &sm.produced, &sm.msum, &sm.msum_ready, cons, n, Tn, lane);
+        if (warp == 0) FccConsumer<T, LP, true>::run(a, sm, n, Tn, lane);
+        else scan_producer<T, true>(a, sm.raw, LP, sm.uring, LP, &sm.produced, &sm.msum, &sm.msum_ready, cons,
+                                    [&](int g) { fcc_flush_group<T, LP, true>(a, sm, n, Tn, g, lane); }, ngroups, n, Tn, lane);
     }
 }
 
@@ -529,21 +748,8 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
 // rate of a lone warp -- packed FMUL2/FFMA2 on position pairs (j, j+4) (the shifted neighbour pair of (j, j+4) is the
 // aligned pair (j-1, j+3)), 32-bit shared-memory addressing for the label gather, pointer-walked stores.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float lds_f32(unsigned addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ float max8(const float2 (&p)[4]) {
     return fmaxf(fmaxf(fmaxf(p[0].x, p[0].y), fmaxf(p[1].x, p[1].y)), fmaxf(fmaxf(p[2].x, p[2].y), fmaxf(p[3].x, p[3].y)));
-}
-
-// exact power of two that brings m (>= 0, finite) into [1,2): scale = 2^-e.  m == 0 or denormal leaves the block alone.
-__device__ __forceinline__ void pow2_fast(float m, float &scale, int &e) {
-    const int eb = __float_as_int(m) >> 23;                // m >= 0: no sign bit
-    const bool live = eb != 0;
-    scale = live ? __int_as_float((254 - eb) << 23) : 1.0f;
-    e = live ? eb - 127 : 0;
 }
 
 // One consumer warp (S <= 256).  Lane boundaries need no special cases: shfl_up/down hand the edge lane its OWN
@@ -788,8 +994,8 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
             for (int q = 0; q < W; ++q) c = min(c, ld_volatile_s32(&sm.consumed[q]));
             return c;
         };
-        if (dir == 0) scan_producer<T, false>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, n, Tn, lane);
-        else scan_producer<T, true>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, n, Tn, lane);
+        if (dir == 0) scan_producer<T, false>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, [](int) {}, 0, n, Tn, lane);
+        else scan_producer<T, true>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, [](int) {}, 0, n, Tn, lane);
         return;
     }
     T h[ASG_BLK], dout[ASG_BLK];
@@ -848,8 +1054,11 @@ template <typename T, int LP>
 static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int ndirs, cudaStream_t st) {
     dim3 grid(a.d.N, ndirs);
     {
+        const size_t bytes = sizeof(FccSmem<T, LP>);
+        cudaError_t e = cudaFuncSetAttribute(fcc_scan_kernel<T, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
         LaunchScope ls(K_FCC_SCAN, st);
-        fcc_scan_kernel<T, LP><<<grid, 64, 0, st>>>(a);
+        fcc_scan_kernel<T, LP><<<grid, 64, bytes, st>>>(a);
     }
     return cudaGetLastError();
 }
