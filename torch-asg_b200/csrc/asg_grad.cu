@@ -93,7 +93,7 @@ __host__ __device__ inline GradMap grad_map(size_t eb, int L, int lpi, int sp, i
     m.o_Gal = take(eb * (size_t)L * L);
     m.o_Gf = take(fcc ? eb * (size_t)L * L : 0);
     m.o_galfix = take(fac ? 8 * 2 * (size_t)L * L : 0);
-    m.o_bins = take(fac ? 8 * (size_t)nw * GRAD_LBINS : 0);
+    m.o_bins = take(fac ? 8 * (size_t)nw * 2 * GRAD_LBINS : 0);
     m.o_acc = take((fac && sp > 256) ? eb * (size_t)nw * 2 * sp : 0);
     m.o_bars = take(sizeof(uint64_t) * 2 * 8);
     m.o_stages = align_up(off, 128);
@@ -116,7 +116,7 @@ __device__ __forceinline__ void lds8(const double *p, double (&v)[8]) {
 }
 
 template <typename T, int LP, bool FCC, bool FAC>
-__global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32) grad_kernel(const GradArgs<T> a) {
+__global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(const GradArgs<T> a) {
     extern __shared__ __align__(128) char smem_raw[];
     typedef typename Fix<T>::bin_t bin_t;
     const int L = a.d.L, N = a.d.N, Tt = a.d.T;
@@ -202,10 +202,10 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32) grad_kernel(const 
     unsigned long long *galfix = (unsigned long long *)(smem_raw + mp.o_galfix);     // [2][L*L] fixed-point edge sums
     for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
 
-    bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * GRAD_LBINS;
+    bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * 2 * GRAD_LBINS;     // two sets: one per frame in flight
     T *acc = (T *)(smem_raw + mp.o_acc) + (size_t)warp * 2 * sp;     // wide mode only: [2][sp] stay / total sums of this warp
     if (FAC) {
-        for (int l = lane; l < GRAD_LBINS; l += 32) bins[l] = 0;
+        for (int l = lane; l < 2 * GRAD_LBINS; l += 32) bins[l] = 0;
         if (!narrow)
             for (int s = lane; s < 2 * sp; s += 32) acc[s] = T(0);
     }
@@ -305,6 +305,132 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32) grad_kernel(const 
         mbar_wait(&full[stage], use & 1);
 
         // smem row r of the alpha arrays = frame t0-1+r (r = 0 is the halo); beta arrays: row r-1 = frame t0-1+r
+        // ---- fast path: both of this warp's frames are live interior frames -> do them together, so that the two
+        //      independent dependency chains (loads, REDUX, shuffle trees, divisions) overlap in one instruction stream
+        if (narrow && TB == 2 * NW && rows_valid == TB && t0 > 0) {
+            const int ra = 1 + warp, rb = 1 + warp + NW;
+            const int rr[2] = {ra, rb};
+            const int lb8 = min(lane, nblk - 1) * 8;          // idle lanes re-read the last block (weight 0)
+            const int le = min(lane, nblk - 1);
+            const bool act = lane < nblk;
+            T bv[2][8];
+            if (FAC) {
+                T av[2][8];
+                int ea[2], eb[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    lds8(sA + rr[u] * sp + lb8, av[u]);
+                    lds8(sB + (rr[u] - 1) * sp + lb8, bv[u]);
+                    ea[u] = sEa[rr[u] * nbp + le];
+                    eb[u] = sEb[(rr[u] - 1) * nbp + le];
+                }
+                T pv[2][8];
+                int ep[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    lds8(sA + (rr[u] - 1) * sp + lb8, pv[u]);
+                    ep[u] = sEa[(rr[u] - 1) * nbp + le];
+                }
+                T ps[2];
+                int c[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bv[u][j] = av[u][j] * (bv[u][j] * Num<T>::prod_scale());
+                    const T pm = tmax(tmax(tmax(bv[u][0], bv[u][1]), tmax(bv[u][2], bv[u][3])), tmax(tmax(bv[u][4], bv[u][5]), tmax(bv[u][6], bv[u][7])));
+                    ps[u] = ((bv[u][0] + bv[u][1]) + (bv[u][2] + bv[u][3])) + ((bv[u][4] + bv[u][5]) + (bv[u][6] + bv[u][7]));
+                    c[u] = (act && pm > T(0)) ? ea[u] + eb[u] : INT_MIN;
+                }
+                const int cmax0 = __reduce_max_sync(ASG_FULL_MASK, c[0]);
+                const int cmax1 = __reduce_max_sync(ASG_FULL_MASK, c[1]);
+                T wgt[2];
+                wgt[0] = (c[0] != INT_MIN && c[0] - cmax0 >= -Num<T>::kMaxShift) ? Num<T>::exp2i(c[0] - cmax0) : T(0);
+                wgt[1] = (c[1] != INT_MIN && c[1] - cmax1 >= -Num<T>::kMaxShift) ? Num<T>::exp2i(c[1] - cmax1) : T(0);
+                T z0 = ps[0] * wgt[0], z1 = ps[1] * wgt[1];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    z0 += __shfl_xor_sync(ASG_FULL_MASK, z0, o);
+                    z1 += __shfl_xor_sync(ASG_FULL_MASK, z1, o);
+                }
+                const T Z[2] = {z0, z1};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const T invZ = (Z[u] > Num<T>::tiny()) ? T(1) / Z[u] : T(0);
+                    const T kq = wgt[u] * FX::kPost;
+                    bin_t *bu = bins + u * GRAD_LBINS;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bv[u][j] = (bv[u][j] * invZ) * kq;
+                        FX::add(&bu[lab[j]], FX::to_fix(bv[u][j]));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    T left = __shfl_up_sync(ASG_FULL_MASK, pv[u][7], 1);
+                    const int el = __shfl_up_sync(ASG_FULL_MASK, ep[u], 1);
+                    left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep[u], Num<T>::kMaxShift - 8));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const T stay = hreg[j] * pv[u][j];
+                        const T den = fma(dreg[j], j ? pv[u][j ? j - 1 : 0] : left, stay);
+                        const T fs = fast_div(stay, tmax(den, Num<T>::tiny()));
+                        accH[j] = fma(bv[u][j], fs, accH[j]);
+                        accQ[j] += bv[u][j];
+                    }
+                }
+                __syncwarp();
+            }
+            T g0[2] = {T(0), T(0)}, g1[2] = {T(0), T(0)};
+            if (FCC) {
+                T inv[2];
+                {
+                    T al0[2], al1[2], be0[2], be1[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        al0[u] = al1[u] = be0[u] = be1[u] = T(0);
+                        if (lane < lpi) { al0[u] = sFa[rr[u] * lpi + lane]; be0[u] = sFb[(rr[u] - 1) * lpi + lane]; }
+                        if (LP > 32 && lane + 32 < lpi) { al1[u] = sFa[rr[u] * lpi + lane + 32]; be1[u] = sFb[(rr[u] - 1) * lpi + lane + 32]; }
+                        g0[u] = al0[u] * be0[u]; g1[u] = al1[u] * be1[u];
+                    }
+                    T z0 = g0[0] + g1[0], z1 = g0[1] + g1[1];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        z0 += __shfl_xor_sync(ASG_FULL_MASK, z0, o);
+                        z1 += __shfl_xor_sync(ASG_FULL_MASK, z1, o);
+                    }
+                    inv[0] = (z0 > T(0)) ? gf / z0 : T(0);
+                    inv[1] = (z1 > T(0)) ? gf / z1 : T(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    g0[u] *= inv[u]; g1[u] *= inv[u];
+                    const T winv = inv[u] * (sc_tma ? sSc[rr[u] - 1] : a.ctx.fcc_scale[(int64_t)n * tp + t0 - 1 + rr[u]]);
+                    T wv[RI], pw[CJ];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) wv[i] = sFw[(rr[u] - 1) * lpi + ib * RI + i] * winv;
+#pragma unroll
+                    for (int j = 0; j < CJ; ++j) pw[j] = sFa[(rr[u] - 1) * lpi + jb * CJ + j];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int j = 0; j < CJ; ++j) G[i][j] = fma(wv[i], pw[j], G[i][j]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                T *gx_row = a.grad_x + ((int64_t)(t0 - 1 + rr[u]) * N + n) * L;
+                T o0 = g0[u], o1 = g1[u];
+                if (FAC) {
+                    bin_t *bu = bins + u * GRAD_LBINS;
+                    const T gs = ga * FX::kInvPost;
+                    if (lane < L) { o0 = fma(gs, FX::from_fix(bu[lane]), o0); bu[lane] = 0; }
+                    if (LP > 32 && lane + 32 < L) { o1 = fma(gs, FX::from_fix(bu[lane + 32]), o1); bu[lane + 32] = 0; }
+                }
+                if (lane < L) gx_row[lane] = o0;
+                if (LP > 32 && lane + 32 < L) gx_row[lane + 32] = o1;
+            }
+            __syncwarp();
+        } else
         for (int r = 1 + warp; r <= TBt; r += NW) {
             const int t = t0 - 1 + r;
             T *gx_row = a.grad_x + ((int64_t)t * N + n) * L;
