@@ -31,7 +31,7 @@
 
 namespace asg {
 
-constexpr int GRAD_MAX_CWARPS = 8;     // consumer warps (+ one producer warp)
+constexpr int GRAD_MAX_CWARPS = 8;     // consumer warps (+ one producer warp); more warps would cap registers below what a frame needs
 constexpr int GRAD_LBINS = 72;         // label bins per warp: L <= 64, bin L = trash (padding positions)
 
 // Fixed-point images (integers add in any order with the same result, so shared-memory atomics stay deterministic):
@@ -584,19 +584,36 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(con
     flush_fac();
     cbar();
 
-    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC): warps add their G slices in order ----
+    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC) ------------------------------------------------------
+    // every warp parks its G slice in the (now idle) tile ring, then each element is summed over the warps in order
     if (FCC) {
-        for (int w = 0; w < NW; ++w) {
-            if (warp == w) {
+        T *Gw = (T *)stages + (size_t)warp * LP * LP;
+        const bool fits = (size_t)NW * LP * LP * sizeof(T) <= mp.stage_bytes * (size_t)NS;
+        if (fits) {
 #pragma unroll
-                for (int i = 0; i < RI; ++i)
+            for (int i = 0; i < RI; ++i)
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) {
-                        const int gi = ib * RI + i, gj = jb * CJ + j;
-                        if (gi < L && gj < L) Gf[gi * L + gj] += G[i][j];
-                    }
-            }
+                for (int j = 0; j < CJ; ++j) Gw[(ib * RI + i) * LP + jb * CJ + j] = G[i][j];
             cbar();
+            for (int e = tid; e < L * L; e += ncons) {
+                const int gi = e / L, gj = e - gi * L;
+                T acc = T(0);
+                for (int w = 0; w < NW; ++w) acc += ((const T *)stages)[(size_t)w * LP * LP + gi * LP + gj];
+                Gf[e] = acc;
+            }
+        } else {
+            for (int w = 0; w < NW; ++w) {
+                if (warp == w) {
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int j = 0; j < CJ; ++j) {
+                            const int gi = ib * RI + i, gj = jb * CJ + j;
+                            if (gi < L && gj < L) Gf[gi * L + gj] += G[i][j];
+                        }
+                }
+                cbar();
+            }
         }
     }
     T *part = a.partials + (size_t)blockIdx.x * L * L;
