@@ -125,7 +125,7 @@ static int grad_typed(int parts, const void *g_full, int64_t gfs, const void *g_
     a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
     a.grad_x = (T *)grad_x; a.grad_A = (T *)grad_A;
     a.partials = (T *)scratch;
-    a.tb = 0; a.nstage = 0; a.nwarps = 0; a.tiles_t = 0; a.num_tiles = 0;
+    a.tb = 0; a.nstage = 0; a.nwarps = 0; a.dry = 0; a.tiles_t = 0; a.num_tiles = 0;
     return launch_grad<T>(a, parts, stream);
 }
 

@@ -113,9 +113,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned by
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     unsigned ok;
     const unsigned addr = smem_u32(bar);
+    // a long suspend-time hint: the thread sleeps in hardware until the phase completes instead of re-polling
+    // (polling warps steal issue slots from the warps they are waiting for)
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
     } while (!ok);
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completion counted on `bar`

@@ -74,6 +74,7 @@ template <typename T> struct GradArgs {
     int tb;                     // frames per tile
     int nstage;                 // depth of the shared-memory tile ring
     int nwarps;                 // consumer warps per CTA
+    int dry;                    // diagnostics: move the data, skip the arithmetic (ASG_GRAD_DRY)
     int tiles_t;                // ceil(T / tb)
     int num_tiles;              // tiles_t * N
 };
