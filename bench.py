@@ -239,8 +239,14 @@ def run_b200(args):
     for i in range(args.warmup):
         step(i)
     sync_all()
+    # kernel ids of the library (asg_kernel_name)
+    kid = {lib.asg_kernel_name(k).decode(): k for k in range(lib.asg_kernel_count())}
     sampler = ClockSampler(local)
     lib.asg_profile_reset()
+    # the timed region carries event pairs only around the kernel whose roofline is reported (two records per step on
+    # the main stream); event pairs around the two concurrent scan kernels would add ~270 us of gaps per step
+    roof_kernel = "grad_kernel" if not fwd_only else "fac_scan_kernel"
+    lib.asg_profile_select(ctypes.c_uint(1 << kid[roof_kernel]))
     lib.asg_profile_enable(1)
     launches0 = lib.asg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,13 +267,27 @@ def run_b200(args):
     ms = float(t.item())
     sampler.join(1.0)
 
-    # per-kernel device time, measured live over the timed region
-    kernels = {}
-    for k in range(lib.asg_kernel_count()):
-        tot, n = ctypes.c_double(), ctypes.c_uint64()
-        lib.asg_profile_read(k, ctypes.byref(tot), ctypes.byref(n))
-        if n.value:
-            kernels[lib.asg_kernel_name(k).decode()] = {"launches": int(n.value), "avg_us": 1e3 * tot.value / n.value}
+    def read_kernels():
+        ks = {}
+        for k in range(lib.asg_kernel_count()):
+            tot, cnt = ctypes.c_double(), ctypes.c_uint64()
+            lib.asg_profile_read(k, ctypes.byref(tot), ctypes.byref(cnt))
+            if cnt.value:
+                ks[lib.asg_kernel_name(k).decode()] = {"launches": int(cnt.value), "avg_us": 1e3 * tot.value / cnt.value}
+        return ks
+
+    kernels = read_kernels()                     # the roofline kernel, timed inside the timed region
+    # every kernel, in a separate short pass (not part of `value`): same steps, event pairs around every launch
+    lib.asg_profile_reset()
+    lib.asg_profile_select(ctypes.c_uint(0xffffffff))
+    lib.asg_profile_enable(1)
+    for i in range(min(args.steps, 50)):
+        step(args.warmup + args.steps + i)
+    sync_all()
+    lib.asg_profile_enable(0)
+    kernels_all = read_kernels()
+    for k, v in kernels_all.items():
+        kernels.setdefault(k, dict(v, note="separate pass"))
 
     out = {
         "metric": METRIC, "value": N * world * args.steps / (ms * 1e-3), "unit": "utterances/s", "n_gpus": world,
@@ -298,7 +318,7 @@ def run_b200(args):
         out["roofline"] = {"bound": "hbm", "kernel": "grad_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                            "frac": ach / peak, "traffic": traffic, "algorithmic_bytes": alg, "peak_source": peak_src,
                            "avg_us": kernels["grad_kernel"]["avg_us"]}
-    else:
+    elif "fac_scan_kernel" in kernels:
         x_bytes = 8 * T * N * L
         ach = x_bytes / (kernels["fac_scan_kernel"]["avg_us"] * 1e-6) / 1e9
         out["roofline"] = {"bound": "hbm", "kernel": "fac_scan_kernel (forward-only: latency-bound serial scan)", "achieved": ach,

@@ -33,7 +33,8 @@
  *
  * Intermediate state is NOT the reference's log-domain alpha/beta: see DESIGN.md "Numerics".  The FCC
  * states are real-domain vectors rescaled by one power of two per frame; the FAC states are block
- * floating point (one power-of-two exponent per 8 target positions per frame).
+ * floating point (one power-of-two exponent per 8 target positions per frame).  All of it is kept in one
+ * array of per-frame records (asg_layout_t).
  */
 #ifndef ASG_B200_H
 #define ASG_B200_H
@@ -73,28 +74,31 @@ enum {
 
 /*
  * Sizes and offsets of the opaque buffers a caller allocates for one (dtype,T,N,L,S) problem.
- * All state is UTTERANCE-MAJOR ([N, tp, ...]): one utterance's frames are contiguous, so the serial scans write
- * one sequential stream each and the gradient assembly fetches a (utterance, frame-range) tile with a handful of
- * contiguous bulk (TMA) copies.  Row pitches are padded so every tile starts 16-byte aligned.
+ *
+ * All per-frame state lives in ONE array of FRAME RECORDS, utterance-major: state[N][tp] records of rec_bytes each,
+ *   record(n,t) = | FAC alpha[sp] | FAC beta[sp] | FAC alpha exponents[nbp] i32 | FAC beta exponents[nbp] i32 |
+ *                 | FCC alpha[lpi] | FCC beta[lpi] | FCC u*beta[lpi] | FCC scale |            (every part 32-byte aligned)
+ * so that (a) each of the four serial scans writes one sequential, sector-aligned stream, and (b) the gradient assembly
+ * fetches a (utterance, frame-range) tile with ONE contiguous bulk (TMA) copy of >= 16 KB -- measured on B200, 1-D bulk
+ * copies cost ~0.37 us apiece and are processed serially per SM, so eight small per-array copies per tile cap a kernel
+ * at ~2.7 TB/s while one 32 KB copy per tile streams at the HBM peak (tools/tma_probe.cu).
  */
 typedef struct asg_layout {
-    int64_t sp;               /* row pitch (elements) of the FAC state arrays: S rounded up to 8 */
+    int64_t sp;               /* FAC row length (elements): S rounded up to 8 */
     int64_t nblk;             /* block exponents per (frame, utterance): sp / 8 */
-    int64_t nbp;              /* row pitch of the exponent arrays: nblk rounded up to 4 */
-    int64_t lpi;              /* row pitch of the FCC state arrays: L rounded up to 4 */
+    int64_t nbp;              /* exponent row length: nblk rounded up to 8 */
+    int64_t lpi;              /* FCC row length: L rounded up to 8 */
     int64_t tp;               /* frame pitch: T rounded up to 4 */
     size_t elem_bytes;        /* 4 or 8 */
-    size_t fcc_state_bytes;   /* one FCC state array  [N,tp,lpi]  */
-    size_t fac_state_bytes;   /* one FAC state array  [N,tp,sp]   */
+    size_t rec_bytes;         /* one frame record (multiple of 32) */
+    size_t state_bytes;       /* the state array: N * tp * rec_bytes */
     size_t ctx_bytes;         /* the context blob handed from asg_scan() to asg_grad() */
     size_t grad_scratch_bytes;/* scratch for asg_grad() (per-CTA partial sums) */
+    /* byte offsets inside a frame record */
+    size_t rec_fac_alpha, rec_fac_beta, rec_fac_ea, rec_fac_eb, rec_fcc_alpha, rec_fcc_beta, rec_fcc_w, rec_fcc_scale;
     /* byte offsets inside the context blob (all 256-byte aligned) */
     size_t off_ehat;          /* [L,L]       exp(A - R)                              */
-    size_t off_fcc_scale;     /* [N,tp]      power-of-two applied to alpha at frame t */
-    size_t off_fcc_w;         /* [N,tp,lpi]  u_t * beta_t (emission-weighted beta)     */
     size_t off_fac_hd;        /* [2,N,sp]    exp(H - Rb), exp(D - Rb)                */
-    size_t off_fac_ea;        /* [N,tp,nbp]  int32 block exponents of FAC alpha      */
-    size_t off_fac_eb;        /* [N,tp,nbp]  int32 block exponents of FAC beta       */
     size_t off_lengths;       /* [2,N] int64 copies of il, tl                        */
     size_t off_scalars;       /* [N,8] float64: per-utterance log-scale bookkeeping (scores in f64 etc.) */
 } asg_layout_t;
@@ -103,11 +107,9 @@ typedef struct asg_layout {
 int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout_t *out);
 
 /*
- * Forward recursions.  Outputs whose role is not selected may be NULL.  fcc_beta / fac_beta may also be
- * NULL when their role IS selected: the beta scans then only produce the scores (forward-only mode,
- * nothing is stored -- fast_asg_gpu_forward_only, streamlined_fast_gpu.cpp:24-94).
- *   fcc_alpha, fcc_beta : [N,tp,lpi] device, dtype (asg_layout_t.fcc_state_bytes each)
- *   fac_alpha, fac_beta : [N,tp,sp]  device, dtype (asg_layout_t.fac_state_bytes each)
+ * Forward recursions.  `state` (state_bytes, device, 256-byte aligned) receives the frame records of the selected
+ * roles; it may be NULL when only beta roles are selected: the beta scans then only produce the scores
+ * (forward-only mode, nothing is stored -- fast_asg_gpu_forward_only, streamlined_fast_gpu.cpp:24-94).
  *   ctx                 : ctx_bytes device (always required)
  *   full_scores         : [N] dtype, written when ASG_ROLE_FCC_BETA is selected
  *   aligned_scores      : [N] dtype, written when ASG_ROLE_FAC_BETA is selected
@@ -119,7 +121,7 @@ int asg_scan(int dtype, int roles,
              const int64_t *y, int64_t y_s0, int64_t y_s1,
              const int64_t *il, const int64_t *tl,
              int64_t T, int64_t N, int64_t L, int64_t S,
-             void *fcc_alpha, void *fcc_beta, void *fac_alpha, void *fac_beta, void *ctx,
+             void *state, void *ctx,
              void *full_scores, void *aligned_scores,
              asg_stream_t stream);
 
@@ -130,13 +132,12 @@ int asg_scan(int dtype, int roles,
  * i.e. the two upstream vectors are applied independently and the FAC part is ADDED, exactly like
  * fast_asg_gpu_backward (streamlined_fast_gpu.cpp:261-287); autograd supplies g_aligned = -g_full.
  * g_full/g_aligned: [N] dtype device, element strides g*_stride (0 = broadcast scalar).
- * `parts` selects FCC only / FAC only / both; unused inputs may be NULL.
+ * `parts` selects FCC only / FAC only / both (the records must hold the matching roles); unused inputs may be NULL.
  */
 int asg_grad(int dtype, int parts,
              const void *g_full, int64_t g_full_stride,
              const void *g_aligned, int64_t g_aligned_stride,
-             const void *fcc_alpha, const void *fcc_beta,
-             const void *fac_alpha, const void *fac_beta, const void *ctx,
+             const void *state, const void *ctx,
              const int64_t *y, int64_t y_s0, int64_t y_s1,
              int64_t T, int64_t N, int64_t L, int64_t S,
              void *grad_x, void *grad_A, void *scratch,
@@ -186,6 +187,9 @@ uint64_t asg_launch_count(void);
  * has no timers.
  */
 int asg_profile_enable(int on);
+/* restrict the timing to the kernel ids whose bit is set (default: all).  Event pairs on the two scan streams cost
+ * far more than the kernels' launch gaps, so a headline run times only the kernel whose roofline it reports. */
+int asg_profile_select(unsigned mask);
 int asg_profile_reset(void);
 int asg_profile_read(int kernel_id, double *total_ms, uint64_t *launches);
 const char *asg_kernel_name(int kernel_id);

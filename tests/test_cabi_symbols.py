@@ -33,7 +33,7 @@ def lib():
 def test_every_declared_symbol_is_exported(lib):
     names = declared_symbols()
     assert {"asg_layout", "asg_scan", "asg_grad", "asg_host_create", "asg_host_destroy", "asg_host_loss", "asg_host_submit", "asg_host_wait",
-            "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_read"} <= set(names)
+            "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_select", "asg_profile_read"} <= set(names)
     for n in names:
         assert hasattr(lib, n), "libasg_b200.so does not export " + n
     assert b"sm_100a" in lib.asg_version()
@@ -48,9 +48,10 @@ def test_sass_is_sm_100a_only():
 
 class Layout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("sp", "nblk", "nbp", "lpi", "tp")] + [
-        (n, ctypes.c_size_t) for n in ("elem_bytes", "fcc_state_bytes", "fac_state_bytes", "ctx_bytes",
-                                       "grad_scratch_bytes", "off_ehat", "off_fcc_scale", "off_fcc_w", "off_fac_hd",
-                                       "off_fac_ea", "off_fac_eb", "off_lengths", "off_scalars")]
+        (n, ctypes.c_size_t) for n in ("elem_bytes", "rec_bytes", "state_bytes", "ctx_bytes", "grad_scratch_bytes",
+                                       "rec_fac_alpha", "rec_fac_beta", "rec_fac_ea", "rec_fac_eb", "rec_fcc_alpha",
+                                       "rec_fcc_beta", "rec_fcc_w", "rec_fcc_scale",
+                                       "off_ehat", "off_fac_hd", "off_lengths", "off_scalars")]
 
 
 def _layout(lib, dt, T, N, L, S):
@@ -62,14 +63,18 @@ def _layout(lib, dt, T, N, L, S):
 def test_layout_and_validation(lib):
     rc, lay = _layout(lib, 0, 1000, 64, 40, 200)
     assert rc == 0
-    assert (lay.sp, lay.nblk, lay.nbp, lay.lpi, lay.tp, lay.elem_bytes) == (200, 25, 28, 40, 1000, 4)
-    assert lay.fcc_state_bytes == 4 * 1000 * 64 * 40
-    assert lay.fac_state_bytes == 4 * 1000 * 64 * 200
-    offs = [lay.off_ehat, lay.off_fcc_scale, lay.off_fcc_w, lay.off_fac_hd, lay.off_fac_ea, lay.off_fac_eb,
-            lay.off_lengths, lay.off_scalars]
+    assert (lay.sp, lay.nblk, lay.nbp, lay.lpi, lay.tp, lay.elem_bytes) == (200, 25, 32, 40, 1000, 4)
+    parts = [lay.rec_fac_alpha, lay.rec_fac_beta, lay.rec_fac_ea, lay.rec_fac_eb, lay.rec_fcc_alpha, lay.rec_fcc_beta,
+             lay.rec_fcc_w, lay.rec_fcc_scale]
+    # one frame record: FAC alpha/beta (2 x 800 B), their exponents (2 x 128 B), FCC alpha/beta/u*beta (3 x 160 B), scale
+    assert parts == [0, 800, 1600, 1728, 1856, 2016, 2176, 2336] and lay.rec_bytes == 2368
+    assert all(p % 32 == 0 for p in parts) and lay.rec_bytes % 32 == 0
+    assert lay.state_bytes == 64 * 1000 * 2368
+    offs = [lay.off_ehat, lay.off_fac_hd, lay.off_lengths, lay.off_scalars]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.ctx_bytes > offs[-1]
     rc, lay = _layout(lib, 1, 7, 3, 5, 3)
-    assert rc == 0 and (lay.sp, lay.nblk, lay.nbp, lay.lpi, lay.tp, lay.elem_bytes) == (8, 1, 4, 8, 8, 8)
+    assert rc == 0 and (lay.sp, lay.nblk, lay.nbp, lay.lpi, lay.tp, lay.elem_bytes) == (8, 1, 8, 8, 8, 8)
+    assert lay.rec_bytes == 64 + 64 + 32 + 32 + 3 * 64 + 32 and lay.state_bytes == 3 * 8 * lay.rec_bytes
     assert _layout(lib, 5, 4, 1, 3, 2)[0] == -1 and b"dtype" in lib.asg_last_error()
     assert _layout(lib, 0, 4, 1, 3, 5)[0] == -2          # S > T
     assert _layout(lib, 0, 4, 0, 3, 2)[0] == -2

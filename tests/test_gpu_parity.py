@@ -268,7 +268,7 @@ def test_c_abi_errors():
     assert lib.asg_layout(0, ctypes.c_int64(0), ctypes.c_int64(1), ctypes.c_int64(3), ctypes.c_int64(1), lay) == -2
     assert lib.asg_scan(0, 15, None, *([ctypes.c_int64(0)] * 3), None, *([ctypes.c_int64(0)] * 2), None,
                         *([ctypes.c_int64(0)] * 2), None, None, ctypes.c_int64(4), ctypes.c_int64(1), ctypes.c_int64(3),
-                        ctypes.c_int64(2), None, None, None, None, None, None, None, None) == -3
+                        ctypes.c_int64(2), None, None, None, None, None) == -3
 
 
 # ----------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ constexpr int PROF_SLOTS = 8192;
 struct ProfRec { cudaEvent_t a, b; int kid; };
 std::mutex g_prof_mu;
 std::atomic<int> g_prof_on{0};
+std::atomic<unsigned> g_prof_mask{0xffffffffu};
 std::vector<ProfRec> g_prof_recs;       // recorded since the last read
 std::vector<ProfRec> g_prof_free;       // recycled event pairs
 double g_prof_ms[K_COUNT] = {0};
@@ -32,7 +33,7 @@ std::atomic<uint64_t> g_kid_launches[K_COUNT];
 LaunchScope::LaunchScope(int kid, cudaStream_t st) : kid_(kid), st_(st), slot_(-1) {
     count_launch();
     g_kid_launches[kid].fetch_add(1, std::memory_order_relaxed);
-    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    if (!g_prof_on.load(std::memory_order_relaxed) || !((g_prof_mask.load(std::memory_order_relaxed) >> kid) & 1u)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if ((int)g_prof_recs.size() >= PROF_SLOTS) return;
     ProfRec r;
@@ -93,34 +94,28 @@ using namespace asg;
 template <typename T>
 static int scan_typed(int roles, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0,
                       int64_t A_s1, const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl,
-                      const asg_layout_t &lay, int64_t Tt, int64_t N, int64_t L, int64_t S, void *fcc_alpha, void *fcc_beta,
-                      void *fac_alpha, void *fac_beta, void *ctx, void *full_scores, void *aligned_scores,
-                      cudaStream_t stream) {
+                      const asg_layout_t &lay, int64_t Tt, int64_t N, int64_t L, int64_t S, void *state, void *ctx,
+                      void *full_scores, void *aligned_scores, cudaStream_t stream) {
     ScanArgs<T> a;
     a.x = (const T *)x; a.x_st = x_st; a.x_sn = x_sn; a.x_sl = x_sl;
     a.A = (const T *)A; a.A_s0 = A_s0; a.A_s1 = A_s1;
     a.y = y; a.y_s0 = y_s0; a.y_s1 = y_s1;
     a.il = il; a.tl = tl;
     a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
-    a.fcc_alpha = (T *)fcc_alpha; a.fcc_beta = (T *)fcc_beta;
-    a.fac_alpha = (T *)fac_alpha; a.fac_beta = (T *)fac_beta;
-    a.ctx = make_ctx<T>(ctx, lay, N);
+    a.ctx = make_ctx<T>(state, ctx, lay, N);
     a.full_scores = (T *)full_scores; a.aligned_scores = (T *)aligned_scores;
     a.dir0 = a.dir1 = 0; a.fcc_dirs = a.fac_dirs = 0;
     return launch_scan<T>(a, roles, stream);
 }
 
 template <typename T>
-static int grad_typed(int parts, const void *g_full, int64_t gfs, const void *g_al, int64_t gas, const void *fcc_alpha,
-                      const void *fcc_beta, const void *fac_alpha, const void *fac_beta, const void *ctx, const int64_t *y,
-                      int64_t y_s0, int64_t y_s1, const asg_layout_t &lay, int64_t Tt, int64_t N, int64_t L, int64_t S,
-                      void *grad_x, void *grad_A, void *scratch, cudaStream_t stream) {
+static int grad_typed(int parts, const void *g_full, int64_t gfs, const void *g_al, int64_t gas, const void *state,
+                      const void *ctx, const int64_t *y, int64_t y_s0, int64_t y_s1, const asg_layout_t &lay, int64_t Tt,
+                      int64_t N, int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch, cudaStream_t stream) {
     GradArgs<T> a;
     a.g_full = (const T *)g_full; a.g_full_stride = gfs;
     a.g_aligned = (const T *)g_al; a.g_aligned_stride = gas;
-    a.fcc_alpha = (const T *)fcc_alpha; a.fcc_beta = (const T *)fcc_beta;
-    a.fac_alpha = (const T *)fac_alpha; a.fac_beta = (const T *)fac_beta;
-    a.ctx = make_ctx<T>(const_cast<void *>(ctx), lay, N);
+    a.ctx = make_ctx<T>(const_cast<void *>(state), const_cast<void *>(ctx), lay, N);
     a.y = y; a.y_s0 = y_s0; a.y_s1 = y_s1;
     a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
     a.grad_x = (T *)grad_x; a.grad_A = (T *)grad_A;
@@ -137,7 +132,7 @@ struct asg_host_ctx {
     char *dev;          // one device slab
     size_t dev_bytes;
     // offsets into the slab
-    size_t o_x, o_A, o_y, o_il, o_tl, o_g, o_gneg, o_fa, o_fb, o_aa, o_ab, o_ctx, o_full, o_al, o_loss, o_gx, o_gA, o_scr;
+    size_t o_x, o_A, o_y, o_il, o_tl, o_g, o_gneg, o_state, o_ctx, o_full, o_al, o_loss, o_gx, o_gA, o_scr;
 };
 
 template <typename T> __global__ void host_loss_kernel(const T *full, const T *aligned, T *loss, int N) {
@@ -160,20 +155,27 @@ int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout
     out->elem_bytes = eb;
     out->sp = (S + ASG_BLK - 1) / ASG_BLK * ASG_BLK;
     out->nblk = out->sp / ASG_BLK;
-    out->nbp = (out->nblk + 3) / 4 * 4;
-    out->lpi = (L + 3) / 4 * 4;
+    out->nbp = (out->nblk + 7) / 8 * 8;
+    out->lpi = (L + 7) / 8 * 8;
     out->tp = (T + 3) / 4 * 4;
-    const size_t NT = (size_t)N * out->tp;
-    out->fcc_state_bytes = eb * NT * out->lpi;
-    out->fac_state_bytes = eb * NT * out->sp;
+    {   // the frame record: every part starts on a 32-byte boundary
+        size_t r = 0;
+        auto part = [&](size_t bytes) { size_t o = r; r = align_up(r + bytes, 32); return o; };
+        out->rec_fac_alpha = part(eb * (size_t)out->sp);
+        out->rec_fac_beta = part(eb * (size_t)out->sp);
+        out->rec_fac_ea = part(sizeof(int) * (size_t)out->nbp);
+        out->rec_fac_eb = part(sizeof(int) * (size_t)out->nbp);
+        out->rec_fcc_alpha = part(eb * (size_t)out->lpi);
+        out->rec_fcc_beta = part(eb * (size_t)out->lpi);
+        out->rec_fcc_w = part(eb * (size_t)out->lpi);
+        out->rec_fcc_scale = part(eb);
+        out->rec_bytes = r;
+    }
+    out->state_bytes = (size_t)N * out->tp * out->rec_bytes;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     out->off_ehat = take(eb * (size_t)L * L);
-    out->off_fcc_scale = take(eb * NT);
-    out->off_fcc_w = take(eb * NT * out->lpi);
     out->off_fac_hd = take(eb * 2 * (size_t)N * out->sp);
-    out->off_fac_ea = take(sizeof(int) * NT * out->nbp);
-    out->off_fac_eb = take(sizeof(int) * NT * out->nbp);
     out->off_lengths = take(sizeof(int64_t) * 2 * (size_t)N);
     out->off_scalars = take(sizeof(double) * 8 * (size_t)N);
     out->ctx_bytes = off;
@@ -185,45 +187,42 @@ int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout
 
 int asg_scan(int dtype, int roles, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0,
              int64_t A_s1, const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl, int64_t T,
-             int64_t N, int64_t L, int64_t S, void *fcc_alpha, void *fcc_beta, void *fac_alpha, void *fac_beta, void *ctx,
-             void *full_scores, void *aligned_scores, asg_stream_t stream) {
+             int64_t N, int64_t L, int64_t S, void *state, void *ctx, void *full_scores, void *aligned_scores,
+             asg_stream_t stream) {
     asg_layout_t lay;
     int rc = asg_layout(dtype, T, N, L, S, &lay);
     if (rc) return rc;
     if ((roles & ~ASG_ROLE_ALL) || roles == 0) return fail(ASG_E_SHAPE, "asg_scan: bad roles mask %d", roles);
     if (!x || !A || !ctx) return fail(ASG_E_NULL, "asg_scan: x, A and ctx are required");
-    if ((roles & ASG_ROLE_FCC_ALPHA) && !fcc_alpha) return fail(ASG_E_NULL, "asg_scan: fcc_alpha is NULL");
-    if ((roles & ASG_ROLE_FAC_ALPHA) && !fac_alpha) return fail(ASG_E_NULL, "asg_scan: fac_alpha is NULL");
+    if ((roles & (ASG_ROLE_FCC_ALPHA | ASG_ROLE_FAC_ALPHA)) && !state) return fail(ASG_E_NULL, "asg_scan: state is NULL (only the beta scans can run without it)");
     if ((roles & (ASG_ROLE_FAC_ALPHA | ASG_ROLE_FAC_BETA)) && !y) return fail(ASG_E_NULL, "asg_scan: y is NULL");
     int e;
     if (dtype == ASG_F32)
-        e = scan_typed<float>(roles, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, lay, T, N, L, S, fcc_alpha,
-                              fcc_beta, fac_alpha, fac_beta, ctx, full_scores, aligned_scores, (cudaStream_t)stream);
+        e = scan_typed<float>(roles, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, lay, T, N, L, S, state, ctx,
+                              full_scores, aligned_scores, (cudaStream_t)stream);
     else
-        e = scan_typed<double>(roles, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, lay, T, N, L, S, fcc_alpha,
-                               fcc_beta, fac_alpha, fac_beta, ctx, full_scores, aligned_scores, (cudaStream_t)stream);
+        e = scan_typed<double>(roles, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, lay, T, N, L, S, state, ctx,
+                               full_scores, aligned_scores, (cudaStream_t)stream);
     return cuda_fail(e, "asg_scan");
 }
 
 int asg_grad(int dtype, int parts, const void *g_full, int64_t g_full_stride, const void *g_aligned,
-             int64_t g_aligned_stride, const void *fcc_alpha, const void *fcc_beta, const void *fac_alpha,
-             const void *fac_beta, const void *ctx, const int64_t *y, int64_t y_s0, int64_t y_s1, int64_t T, int64_t N,
-             int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch, asg_stream_t stream) {
+             int64_t g_aligned_stride, const void *state, const void *ctx, const int64_t *y, int64_t y_s0, int64_t y_s1,
+             int64_t T, int64_t N, int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch, asg_stream_t stream) {
     asg_layout_t lay;
     int rc = asg_layout(dtype, T, N, L, S, &lay);
     if (rc) return rc;
     if (parts < 1 || parts > 3) return fail(ASG_E_SHAPE, "asg_grad: bad parts mask %d", parts);
-    if (!ctx || !grad_x || !grad_A || !scratch) return fail(ASG_E_NULL, "asg_grad: ctx, grad_x, grad_A, scratch are required");
-    if ((parts & ASG_PART_FCC) && (!g_full || !fcc_alpha || !fcc_beta)) return fail(ASG_E_NULL, "asg_grad: FCC inputs missing");
-    if ((parts & ASG_PART_FAC) && (!g_aligned || !fac_alpha || !fac_beta || !y))
-        return fail(ASG_E_NULL, "asg_grad: FAC inputs missing");
+    if (!state || !ctx || !grad_x || !grad_A || !scratch) return fail(ASG_E_NULL, "asg_grad: state, ctx, grad_x, grad_A, scratch are required");
+    if ((parts & ASG_PART_FCC) && !g_full) return fail(ASG_E_NULL, "asg_grad: g_full is NULL");
+    if ((parts & ASG_PART_FAC) && (!g_aligned || !y)) return fail(ASG_E_NULL, "asg_grad: FAC inputs missing");
     int e;
     if (dtype == ASG_F32)
-        e = grad_typed<float>(parts, g_full, g_full_stride, g_aligned, g_aligned_stride, fcc_alpha, fcc_beta, fac_alpha,
-                              fac_beta, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch, (cudaStream_t)stream);
+        e = grad_typed<float>(parts, g_full, g_full_stride, g_aligned, g_aligned_stride, state, ctx, y, y_s0, y_s1, lay, T, N, L, S,
+                              grad_x, grad_A, scratch, (cudaStream_t)stream);
     else
-        e = grad_typed<double>(parts, g_full, g_full_stride, g_aligned, g_aligned_stride, fcc_alpha, fcc_beta, fac_alpha,
-                               fac_beta, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch, (cudaStream_t)stream);
+        e = grad_typed<double>(parts, g_full, g_full_stride, g_aligned, g_aligned_stride, state, ctx, y, y_s0, y_s1, lay, T, N, L, S,
+                               grad_x, grad_A, scratch, (cudaStream_t)stream);
     return cuda_fail(e, "asg_grad");
 }
 
@@ -253,10 +252,7 @@ int asg_host_create(int dtype, int device, int64_t T, int64_t N, int64_t L, int6
     h->o_tl = take(8 * (size_t)N);
     h->o_g = take(eb * (size_t)N);
     h->o_gneg = take(eb * (size_t)N);
-    h->o_fa = take(h->lay.fcc_state_bytes);
-    h->o_fb = take(h->lay.fcc_state_bytes);
-    h->o_aa = take(h->lay.fac_state_bytes);
-    h->o_ab = take(h->lay.fac_state_bytes);
+    h->o_state = take(h->lay.state_bytes);
     h->o_ctx = take(h->lay.ctx_bytes);
     h->o_full = take(eb * (size_t)N);
     h->o_al = take(eb * (size_t)N);
@@ -300,7 +296,7 @@ int asg_host_submit(asg_host_ctx_t *h, const void *x, const void *A, const int64
     const int roles = want_grad ? ASG_ROLE_ALL : ASG_ROLE_FORWARD_ONLY;
     int rc = asg_scan(h->dtype, roles, d + h->o_x, N * L, L, 1, d + h->o_A, L, 1, (const int64_t *)(d + h->o_y), S, 1,
                       il ? (const int64_t *)(d + h->o_il) : nullptr, tl ? (const int64_t *)(d + h->o_tl) : nullptr, T, N, L, S,
-                      d + h->o_fa, d + h->o_fb, d + h->o_aa, d + h->o_ab, d + h->o_ctx, d + h->o_full, d + h->o_al, st);
+                      want_grad ? d + h->o_state : nullptr, d + h->o_ctx, d + h->o_full, d + h->o_al, st);
     if (rc) return rc;
     const int nb = (int)((N + 127) / 128);
     if (h->dtype == ASG_F32) host_loss_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_full), (float *)(d + h->o_al), (float *)(d + h->o_loss), (int)N);
@@ -311,9 +307,8 @@ int asg_host_submit(asg_host_ctx_t *h, const void *x, const void *A, const int64
         if (h->dtype == ASG_F32) host_g_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_g), (float *)(d + h->o_g), (float *)(d + h->o_gneg), (int)N, g != nullptr);
         else host_g_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_g), (double *)(d + h->o_g), (double *)(d + h->o_gneg), (int)N, g != nullptr);
         { LaunchScope ls(K_HOST_MISC, st); }
-        rc = asg_grad(h->dtype, ASG_PART_BOTH, d + h->o_g, 1, d + h->o_gneg, 1, d + h->o_fa, d + h->o_fb, d + h->o_aa,
-                      d + h->o_ab, d + h->o_ctx, (const int64_t *)(d + h->o_y), S, 1, T, N, L, S, d + h->o_gx, d + h->o_gA,
-                      d + h->o_scr, st);
+        rc = asg_grad(h->dtype, ASG_PART_BOTH, d + h->o_g, 1, d + h->o_gneg, 1, d + h->o_state, d + h->o_ctx,
+                      (const int64_t *)(d + h->o_y), S, 1, T, N, L, S, d + h->o_gx, d + h->o_gA, d + h->o_scr, st);
         if (rc) return rc;
         if (grad_x) ASG_TRY(cudaMemcpyAsync(grad_x, d + h->o_gx, eb * (size_t)T * N * L, cudaMemcpyDeviceToHost, st), "D2H grad_x");
         if (grad_A) ASG_TRY(cudaMemcpyAsync(grad_A, d + h->o_gA, eb * (size_t)L * L, cudaMemcpyDeviceToHost, st), "D2H grad_A");
@@ -342,7 +337,20 @@ uint64_t asg_launch_count(void) { return g_launches.load(std::memory_order_relax
 
 int asg_profile_enable(int on) {
     if (!on) prof_drain();
+    if (on) {   // create the event pairs up front: cudaEventCreate costs tens of microseconds and must stay out of timed loops
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        while ((int)(g_prof_free.size() + g_prof_recs.size()) < PROF_SLOTS) {
+            ProfRec r;
+            if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) break;
+            r.kid = 0;
+            g_prof_free.push_back(r);
+        }
+    }
     g_prof_on.store(on ? 1 : 0);
+    return 0;
+}
+int asg_profile_select(unsigned mask) {
+    g_prof_mask.store(mask);
     return 0;
 }
 int asg_profile_reset(void) {

@@ -64,26 +64,18 @@ template <> struct Fix<double> {
 __device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 
-// shared-memory map: [per-CTA block][stage 0][stage 1]...
+// shared-memory map: [per-CTA block][stage 0][stage 1]...   A stage holds TB+1 frame records (the halo record of
+// frame t0-1 first) exactly as they lie in global memory, plus the tile's winv scalars.
 struct GradMap {
-    // per stage, byte offsets from the stage base
-    size_t oA, oB, oEa, oEb, oFa, oFb, oFw, oSc, oWinv, stage_bytes;
-    // per CTA, byte offsets from the base
-    size_t o_hh, o_din, o_ylab, o_Gal, o_Gf, o_galfix, o_bins, o_acc, o_bars, o_stages, total;
+    size_t oRec, oWinv, stage_bytes;                                   // per stage, byte offsets from the stage base
+    size_t o_hh, o_din, o_ylab, o_Gal, o_Gf, o_galfix, o_bins, o_acc, o_bars, o_stages, total;   // per CTA
 };
 
-__host__ __device__ inline GradMap grad_map(size_t eb, int L, int lpi, int sp, int nbp, int TB, int nstage, int nw, bool fcc, bool fac) {
+__host__ __device__ inline GradMap grad_map(size_t eb, size_t rec_bytes, int L, int sp, int TB, int nstage, int nw, bool fcc, bool fac) {
     GradMap m;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
-    m.oA = take(fac ? eb * (size_t)(TB + 1) * sp : 0);
-    m.oB = take(fac ? eb * (size_t)TB * sp : 0);
-    m.oEa = take(fac ? sizeof(int) * (size_t)(TB + 1) * nbp : 0);
-    m.oEb = take(fac ? sizeof(int) * (size_t)TB * nbp : 0);
-    m.oFa = take(fcc ? eb * (size_t)(TB + 1) * lpi : 0);
-    m.oFb = take(fcc ? eb * (size_t)TB * lpi : 0);
-    m.oFw = take(fcc ? eb * (size_t)TB * lpi : 0);
-    m.oSc = take(fcc ? eb * (size_t)((TB + 3) / 4 * 4) : 0);
+    m.oRec = take(rec_bytes * (size_t)(TB + 1));
     m.oWinv = take(fcc ? eb * (size_t)((TB + 3) / 4 * 4) : 0);
     m.stage_bytes = align_up(off, 128);
     off = 0;
@@ -132,10 +124,10 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
     const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp, lpi = (int)a.ctx.lpi;
     const int64_t tp = a.ctx.tp;
     const int TB = a.tb, NS = a.nstage;
-    const GradMap mp = grad_map(sizeof(T), L, lpi, sp, nbp, TB, NS, NF, FCC, FAC);
+    const GradMap mp = grad_map(sizeof(T), (size_t)a.ctx.R, L, sp, TB, NS, NF, FCC, FAC);
+    const int R = (int)a.ctx.R;                    // frame record size in bytes
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nframe = NF * 32;                    // threads of the frame warps (named barrier 1)
-    const bool sc_tma = (TB % 4) == 0;             // the per-frame scales ride the ring only when tile starts are 16-byte aligned
 
     T *hh = (T *)(smem_raw + mp.o_hh), *din = (T *)(smem_raw + mp.o_din);
     T *Gal = (T *)(smem_raw + mp.o_Gal);
@@ -153,49 +145,31 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
     }
     __syncthreads();
 
-    // =========================== producer warp: bulk copies into the ring ===========================
-    // lane 0 owns the barriers; lanes 0..7 each issue one of the tile's eight bulk copies
+    // =========================== producer warp: ONE bulk copy per tile ================================
+    // records t0-1 .. t0+rows-1 of the utterance are one contiguous chunk of the state array
     if (warp == NF + NO) {
-        int n = q_begin / a.tiles_t, tt = q_begin - n * a.tiles_t;     // walked, no per-tile divisions
-        int Tn = (q_begin < q_end) ? (int)a.ctx.il[n] : 0;
-        int stage = 0, use = 0;
-        for (int q = q_begin; q < q_end; ++q) {
-            const int t0 = tt * TB;
-            const int TBt = min(TB, Tt - t0);
-            const int rows = max(0, min(TBt, Tn - t0));
-            if (lane == 0) mbar_wait(&empty[stage], (use & 1) ^ 1);
-            __syncwarp();
-            if (rows == 0) {
-                if (lane == 0) mbar_arrive(&full[stage]);
-            } else {
-                char *sb = stages + (size_t)stage * mp.stage_bytes;
-                const int prev = t0 > 0 ? 1 : 0;                   // the halo row t0-1 exists
-                const int64_t rowc = (int64_t)n * tp + t0;           // first current row
-                const int64_t rowa = rowc - prev;                    // first alpha row fetched
-                const unsigned na = (unsigned)(rows + prev);
-                const unsigned nsc = (unsigned)((rows + 3) / 4 * 4);
-                if (lane == 0) {
-                    unsigned bytes = 0;
-                    if (FAC) bytes += (unsigned)(sizeof(T) * (na + rows) * sp + sizeof(int) * (na + rows) * nbp);
-                    if (FCC) bytes += (unsigned)(sizeof(T) * ((na + 2 * rows) * lpi + (sc_tma ? nsc : 0)));
+        if (lane == 0) {
+            int n = q_begin / a.tiles_t, tt = q_begin - n * a.tiles_t;     // walked, no per-tile divisions
+            int Tn = (q_begin < q_end) ? (int)a.ctx.il[n] : 0;
+            int stage = 0, use = 0;
+            for (int q = q_begin; q < q_end; ++q) {
+                const int t0 = tt * TB;
+                const int TBt = min(TB, Tt - t0);
+                const int rows = max(0, min(TBt, Tn - t0));
+                mbar_wait(&empty[stage], (use & 1) ^ 1);
+                if (rows == 0) {
+                    mbar_arrive(&full[stage]);
+                } else {
+                    char *sb = stages + (size_t)stage * mp.stage_bytes;
+                    const int prev = t0 > 0 ? 1 : 0;                   // the halo record t0-1 exists
+                    const int64_t rowa = (int64_t)n * tp + t0 - prev;    // first record fetched
+                    const unsigned bytes = (unsigned)(rows + prev) * (unsigned)R;
                     mbar_arrive_expect_tx(&full[stage], bytes);
+                    bulk_g2s(sb + mp.oRec + (size_t)(1 - prev) * R, a.ctx.record(rowa), bytes, &full[stage]);
                 }
-                __syncwarp();
-                if (FAC) {
-                    if (lane == 0) bulk_g2s(sb + mp.oA + sizeof(T) * (size_t)(1 - prev) * sp, a.fac_alpha + rowa * sp, (unsigned)(sizeof(T) * na * sp), &full[stage]);
-                    if (lane == 1) bulk_g2s(sb + mp.oB, a.fac_beta + rowc * sp, (unsigned)(sizeof(T) * rows * sp), &full[stage]);
-                    if (lane == 2) bulk_g2s(sb + mp.oEa + sizeof(int) * (size_t)(1 - prev) * nbp, a.ctx.fac_ea + rowa * nbp, (unsigned)(sizeof(int) * na * nbp), &full[stage]);
-                    if (lane == 3) bulk_g2s(sb + mp.oEb, a.ctx.fac_eb + rowc * nbp, (unsigned)(sizeof(int) * rows * nbp), &full[stage]);
-                }
-                if (FCC) {
-                    if (lane == 4) bulk_g2s(sb + mp.oFa + sizeof(T) * (size_t)(1 - prev) * lpi, a.fcc_alpha + rowa * lpi, (unsigned)(sizeof(T) * na * lpi), &full[stage]);
-                    if (lane == 5) bulk_g2s(sb + mp.oFb, a.fcc_beta + rowc * lpi, (unsigned)(sizeof(T) * rows * lpi), &full[stage]);
-                    if (lane == 6) bulk_g2s(sb + mp.oFw, a.ctx.fcc_w + rowc * lpi, (unsigned)(sizeof(T) * rows * lpi), &full[stage]);
-                    if (lane == 7 && sc_tma) bulk_g2s(sb + mp.oSc, a.ctx.fcc_scale + rowc, (unsigned)(sizeof(T) * nsc), &full[stage]);
-                }
+                if (++stage == NS) { stage = 0; ++use; }
+                if (++tt == a.tiles_t) { tt = 0; ++n; if (q + 1 < q_end) Tn = (int)a.ctx.il[n]; }
             }
-            if (++stage == NS) { stage = 0; ++use; }
-            if (++tt == a.tiles_t) { tt = 0; ++n; if (q + 1 < q_end) Tn = (int)a.ctx.il[n]; }
         }
         return;
     }
@@ -219,15 +193,17 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
             if (n != cur_n) { cur_n = n; Tn = (int)a.ctx.il[n]; }
             const int rows_valid = max(0, min(TBt, Tn - t0));
             char *sb = stages + (size_t)stage * mp.stage_bytes;
-            const T *sFa = (const T *)(sb + mp.oFa), *sFw = (const T *)(sb + mp.oFw), *sWi = (const T *)(sb + mp.oWinv);
+            const char *srec = sb + mp.oRec;
+            const T *sWi = (const T *)(sb + mp.oWinv);
             mbar_wait(&full[stage], use & 1);
             mbar_wait(&mid[stage], use & 1);                       // every frame warp has published its winv
             for (int r = (t0 > 0 ? 1 : 2); r <= rows_valid && !a.dry; ++r) {   // frame 0 has no incoming edge
                 const T winv = sWi[r - 1];
                 T wv[8];
-                lds8(sFw + (r - 1) * lpi + o * 8, wv);
-                const T p0 = c0 ? sFa[(r - 1) * lpi + lane] * winv : T(0);
-                const T p1 = c1 ? sFa[(r - 1) * lpi + lane + 32] * winv : T(0);
+                lds8((const T *)(srec + (size_t)r * R + a.ctx.o_cw) + o * 8, wv);                 // u o beta of frame t
+                const T *pa = (const T *)(srec + (size_t)(r - 1) * R + a.ctx.o_ca);                 // alpha of frame t-1
+                const T p0 = c0 ? pa[lane] * winv : T(0);
+                const T p1 = c1 ? pa[lane + 32] * winv : T(0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { G0[i] = fma(wv[i], p0, G0[i]); if (LP > 32) G1[i] = fma(wv[i], p1, G1[i]); }
             }
@@ -351,9 +327,7 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
         }
         const int rows_valid = max(0, min(TBt, Tn - t0));   // frames t0 .. t0+rows_valid-1 are inside the utterance
         char *sb = stages + (size_t)stage * mp.stage_bytes;
-        const T *sA = (const T *)(sb + mp.oA), *sB = (const T *)(sb + mp.oB);
-        const int *sEa = (const int *)(sb + mp.oEa), *sEb = (const int *)(sb + mp.oEb);
-        const T *sFa = (const T *)(sb + mp.oFa), *sFb = (const T *)(sb + mp.oFb), *sSc = (const T *)(sb + mp.oSc);
+        const char *srec = sb + mp.oRec;
         T *sWi = (T *)(sb + mp.oWinv);
 
         mbar_wait(&full[stage], use & 1);
@@ -368,16 +342,20 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                 continue;
             }
             // ---------------- FCC posterior first: the outer-product warps wait for winv ----------------
+            const char *rec = srec + (size_t)r * R;           // this frame's record; rec - R is frame t-1's
+            const T *sA = (const T *)(rec + a.ctx.o_fa), *sB = (const T *)(rec + a.ctx.o_fb), *sAp = (const T *)(rec - R + a.ctx.o_fa);
+            const int *sEa = (const int *)(rec + a.ctx.o_ea), *sEb = (const int *)(rec + a.ctx.o_eb), *sEp = (const int *)(rec - R + a.ctx.o_ea);
             T g0 = T(0), g1 = T(0);
             if (FCC) {
+                const T *sFa = (const T *)(rec + a.ctx.o_ca), *sFb = (const T *)(rec + a.ctx.o_cb);
                 T al0 = T(0), al1 = T(0), be0 = T(0), be1 = T(0);
-                if (lane < lpi) { al0 = sFa[r * lpi + lane]; be0 = sFb[(r - 1) * lpi + lane]; }
-                if (LP > 32 && lane + 32 < lpi) { al1 = sFa[r * lpi + lane + 32]; be1 = sFb[(r - 1) * lpi + lane + 32]; }
+                if (lane < lpi) { al0 = sFa[lane]; be0 = sFb[lane]; }
+                if (LP > 32 && lane + 32 < lpi) { al1 = sFa[lane + 32]; be1 = sFb[lane + 32]; }
                 g0 = al0 * be0; g1 = al1 * be1;
                 const T Z = warp_sum(g0 + g1);
                 const T inv = (Z > T(0)) ? gf / Z : T(0);
                 g0 *= inv; g1 *= inv;
-                if (lane == 0) sWi[r - 1] = (t >= 1) ? inv * (sc_tma ? sSc[r - 1] : a.ctx.fcc_scale[(int64_t)n * tp + t]) : T(0);
+                if (lane == 0) sWi[r - 1] = (t >= 1) ? inv * *(const T *)(rec + a.ctx.o_sc) : T(0);
             }
             if (r + NF > TBt) {                         // this warp's last frame of the tile: winv is out
                 __syncwarp();
@@ -391,9 +369,9 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     const int le = min(lane, nblk - 1);
                     const bool act = lane < nblk;
                     T av[8], bv[8];
-                    lds8(sA + r * sp + lb8, av);
-                    lds8(sB + (r - 1) * sp + lb8, bv);
-                    const int ea = sEa[r * nbp + le], eb = sEb[(r - 1) * nbp + le];
+                    lds8(sA + lb8, av);
+                    lds8(sB + lb8, bv);
+                    const int ea = sEa[le], eb = sEb[le];
                     // alpha and beta mantissas are normalised separately (block maxima in [1,2)), so where one peaks the
                     // other can be ~2^-100: the products carry a constant 2^120 (2^960) so they stay normal numbers
 #pragma unroll
@@ -414,8 +392,8 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     }
                     if (t >= 1) {
                         T pv[8];
-                        lds8(sA + (r - 1) * sp + lb8, pv);
-                        const int ep = sEa[(r - 1) * nbp + le];
+                        lds8(sAp + lb8, pv);
+                        const int ep = sEp[le];
                         // the left neighbour's last value, expressed in this block's exponent (bounded so den stays finite)
                         T left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
                         const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
@@ -435,20 +413,20 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     int cmax = INT_MIN;
                     for (int b = lane; b < nblk; b += 32) {
                         T av[8], bv[8];
-                        lds8(sA + (size_t)r * sp + b * 8, av);
-                        lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
+                        lds8(sA + b * 8, av);
+                        lds8(sB + b * 8, bv);
                         T pm = T(0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) pm = tmax(pm, av[j] * (bv[j] * Num<T>::prod_scale()));
-                        if (pm > T(0)) cmax = max(cmax, sEa[r * nbp + b] + sEb[(r - 1) * nbp + b]);
+                        if (pm > T(0)) cmax = max(cmax, sEa[b] + sEb[b]);
                     }
                     cmax = __reduce_max_sync(ASG_FULL_MASK, cmax);
                     T zs = T(0);
                     for (int b = lane; b < nblk; b += 32) {
                         T av[8], bv[8];
-                        lds8(sA + (size_t)r * sp + b * 8, av);
-                        lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
-                        const int c = sEa[r * nbp + b] + sEb[(r - 1) * nbp + b];
+                        lds8(sA + b * 8, av);
+                        lds8(sB + b * 8, bv);
+                        const int c = sEa[b] + sEb[b];
                         T pm = T(0), ps = T(0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { const T p = av[j] * (bv[j] * Num<T>::prod_scale()); pm = tmax(pm, p); ps += p; }
@@ -458,9 +436,9 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
                     for (int b = lane; b < nblk; b += 32) {
                         T av[8], bv[8];
-                        lds8(sA + (size_t)r * sp + b * 8, av);
-                        lds8(sB + (size_t)(r - 1) * sp + b * 8, bv);
-                        const int c = sEa[r * nbp + b] + sEb[(r - 1) * nbp + b];
+                        lds8(sA + b * 8, av);
+                        lds8(sB + b * 8, bv);
+                        const int c = sEa[b] + sEb[b];
                         T pm = T(0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * (bv[j] * Num<T>::prod_scale())) * invZ; pm = tmax(pm, bv[j]); }
@@ -469,10 +447,9 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                         if (wgt == T(0)) continue;
                         T pv[8], left = T(0);
                         if (t >= 1) {
-                            lds8(sA + (size_t)(r - 1) * sp + b * 8, pv);
+                            lds8(sAp + b * 8, pv);
                             if (b > 0)
-                                left = sA[(size_t)(r - 1) * sp + b * 8 - 1] *
-                                       Num<T>::exp2i(min(sEa[(r - 1) * nbp + b - 1] - sEa[(r - 1) * nbp + b], Num<T>::kMaxShift - 8));
+                                left = sAp[b * 8 - 1] * Num<T>::exp2i(min(sEp[b - 1] - sEp[b], Num<T>::kMaxShift - 8));
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -559,7 +536,7 @@ int grad_grid_size(int device) {
 template <typename T, int LP, bool FCC, bool FAC>
 static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     GradArgs<T> a = a_in;
-    const int L = a.d.L, sp = (int)a.ctx.sp, nbp = (int)a.ctx.nbp, lpi = (int)a.ctx.lpi;
+    const int L = a.d.L, sp = (int)a.ctx.sp;
     int device = 0;
     cudaGetDevice(&device);
     // (frames per tile, ring depth): one persistent CTA per SM, one frame per frame warp, as much in flight as fits
@@ -576,7 +553,7 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
         for (int ni = 0; ni < 6 && !tb; ++ni) {
             if (force_ns && nss[ni] != force_ns) continue;
             if (ti == 0 && nss[ni] < 2 && tbs[1] < NF) continue;     // prefer a shorter tile over an unpipelined ring
-            const size_t b = grad_map(sizeof(T), L, lpi, sp, nbp, tbs[ti], nss[ni], NF, FCC, FAC).total;
+            const size_t b = grad_map(sizeof(T), (size_t)a.ctx.R, L, sp, tbs[ti], nss[ni], NF, FCC, FAC).total;
             if (b <= 227 * 1024) { tb = tbs[ti]; ns = nss[ni]; bytes = b; }
         }
     }

@@ -6,33 +6,41 @@
 
 namespace asg {
 
-// typed view of the context blob (see asg_layout_t)
+// typed view of the frame-record array + the context blob (see asg_layout_t)
 template <typename T> struct Ctx {
+    char *rec;        // [N,tp] frame records
+    int64_t R;        // record size in bytes
+    int o_fa, o_fb, o_ea, o_eb, o_ca, o_cb, o_cw, o_sc;   // byte offsets of the parts inside a record
     T *ehat;          // [L,L]
-    T *fcc_scale;     // [N,tp]
-    T *fcc_w;         // [N,tp,lpi]
     T *fac_hd;        // [2,N,sp]   h_s, d_s (edge s -> s+1)
-    int *fac_ea;      // [N,tp,nbp]
-    int *fac_eb;      // [N,tp,nbp]
     int64_t *il;      // [N]
     int64_t *tl;      // [N]
     double *scalars;  // [N,8]
     int64_t sp, nblk, nbp, lpi, tp;
+    __host__ __device__ __forceinline__ char *record(int64_t row) const { return rec + row * R; }
+    __host__ __device__ __forceinline__ T *fac_alpha(int64_t row) const { return (T *)(rec + row * R + o_fa); }
+    __host__ __device__ __forceinline__ T *fac_beta(int64_t row) const { return (T *)(rec + row * R + o_fb); }
+    __host__ __device__ __forceinline__ int *fac_ea(int64_t row) const { return (int *)(rec + row * R + o_ea); }
+    __host__ __device__ __forceinline__ int *fac_eb(int64_t row) const { return (int *)(rec + row * R + o_eb); }
+    __host__ __device__ __forceinline__ T *fcc_alpha(int64_t row) const { return (T *)(rec + row * R + o_ca); }
+    __host__ __device__ __forceinline__ T *fcc_beta(int64_t row) const { return (T *)(rec + row * R + o_cb); }
+    __host__ __device__ __forceinline__ T *fcc_w(int64_t row) const { return (T *)(rec + row * R + o_cw); }
+    __host__ __device__ __forceinline__ T *fcc_scale(int64_t row) const { return (T *)(rec + row * R + o_sc); }
 };
 
 // per-utterance float64 bookkeeping slots in Ctx::scalars
 enum { SC_R = 0, SC_FULL_BETA = 1, SC_FULL_ALPHA = 2, SC_RB = 3, SC_AL_BETA = 4, SC_AL_ALPHA = 5,
        SC_FCC_LOGSCALE_END = 6, SC_SPARE = 7 };
 
-template <typename T> inline Ctx<T> make_ctx(void *blob, const asg_layout_t &lay, int64_t N) {
+template <typename T> inline Ctx<T> make_ctx(void *state, void *blob, const asg_layout_t &lay, int64_t N) {
     char *b = static_cast<char *>(blob);
     Ctx<T> c;
+    c.rec = static_cast<char *>(state);
+    c.R = (int64_t)lay.rec_bytes;
+    c.o_fa = (int)lay.rec_fac_alpha; c.o_fb = (int)lay.rec_fac_beta; c.o_ea = (int)lay.rec_fac_ea; c.o_eb = (int)lay.rec_fac_eb;
+    c.o_ca = (int)lay.rec_fcc_alpha; c.o_cb = (int)lay.rec_fcc_beta; c.o_cw = (int)lay.rec_fcc_w; c.o_sc = (int)lay.rec_fcc_scale;
     c.ehat = reinterpret_cast<T *>(b + lay.off_ehat);
-    c.fcc_scale = reinterpret_cast<T *>(b + lay.off_fcc_scale);
-    c.fcc_w = reinterpret_cast<T *>(b + lay.off_fcc_w);
     c.fac_hd = reinterpret_cast<T *>(b + lay.off_fac_hd);
-    c.fac_ea = reinterpret_cast<int *>(b + lay.off_fac_ea);
-    c.fac_eb = reinterpret_cast<int *>(b + lay.off_fac_eb);
     c.il = reinterpret_cast<int64_t *>(b + lay.off_lengths);
     c.tl = c.il + N;
     c.scalars = reinterpret_cast<double *>(b + lay.off_scalars);
@@ -54,9 +62,7 @@ template <typename T> struct ScanArgs {
     const int64_t *y; int64_t y_s0, y_s1;
     const int64_t *il, *tl;     // may be NULL
     Dims d;
-    T *fcc_alpha, *fcc_beta;    // [N,tp,lpi]
-    T *fac_alpha, *fac_beta;    // [N,tp,sp]
-    Ctx<T> ctx;
+    Ctx<T> ctx;                 // ctx.rec == nullptr: forward-only, nothing is stored
     T *full_scores, *aligned_scores;
     int dir0, dir1;             // direction (0 = alpha, 1 = beta) served by blockIdx.y = 0 / 1
     int fcc_dirs, fac_dirs;     // bit d set: that lattice runs direction d
@@ -65,7 +71,6 @@ template <typename T> struct ScanArgs {
 template <typename T> struct GradArgs {
     const T *g_full; int64_t g_full_stride;
     const T *g_aligned; int64_t g_aligned_stride;
-    const T *fcc_alpha, *fcc_beta, *fac_alpha, *fac_beta;
     Ctx<T> ctx;
     const int64_t *y; int64_t y_s0, y_s1;
     Dims d;

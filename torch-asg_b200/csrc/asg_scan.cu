@@ -256,7 +256,7 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
     // group bookkeeping at k % FB == 0: frames < k are finished (their u slots may be refilled, their state rows may
     // leave); frames k .. k+FB-1 must be in the u ring; the state slots about to be overwritten must have left.
     auto group_sync = [&](int k) {
-        fence_proxy_async();                                    // this lane's ring writes -> visible to the bulk stores
+        __threadfence_block();                                  // this lane's ring rows are visible before `consumed` moves
         __syncwarp();
         if (lane == 0) st_volatile_s32(&sm.consumed, k);
         const int need = min(k + FB, Tn);
@@ -312,7 +312,7 @@ __device__ void fcc_consumer(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, in
         publish(k, v1, v2, w1, w2, applied);
         __syncwarp();
     }
-    fence_proxy_async();
+    __threadfence_block();
     __syncwarp();
     if (lane == 0) st_volatile_s32(&sm.consumed, Tn);
 
@@ -397,7 +397,7 @@ __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &s
     T f1 = T(0), f2 = T(0);
 
     auto group_sync = [&](int k) {
-        fence_proxy_async();
+        __threadfence_block();
         __syncwarp();
         if (lane == 0) st_volatile_s32(&sm.consumed, k);
         const int need = min(k + FB, Tn);
@@ -472,7 +472,7 @@ __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &s
         publish(k, v1, v2, w1, w2, applied);
         __syncwarp();
     }
-    fence_proxy_async();
+    __threadfence_block();
     __syncwarp();
     if (lane == 0) st_volatile_s32(&sm.consumed, Tn);
 
@@ -498,35 +498,32 @@ template <int LP, bool BETA> struct FccConsumer<float, LP, BETA> {
     }
 };
 
-// producer-side: group g of finished state rows -> global memory, with bulk (TMA) stores
+// producer-side: group g of finished state rows leaves the shared-memory rings for the frame records
+// (16-byte vector stores by the whole producer warp; a record part is one contiguous, sector-aligned run)
 template <typename T, int LP, bool BETA>
 __device__ __forceinline__ void fcc_flush_group(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int g, int lane) {
-    const int lpi = (int)a.ctx.lpi;
     const int rows = min(FB, Tn - g * FB);
-    T *st = BETA ? a.fcc_beta : a.fcc_alpha;
-    if (lane == 0) {
-        if (st != nullptr) {
-            const int s0 = (g % PRG) * FB + (BETA ? FB - rows : 0);           // first ring slot of the run (ascending frames)
-            const int t0 = BETA ? (Tn - g * FB - rows) : g * FB;                // first frame of the run
-            const int64_t grow = (int64_t)n * a.ctx.tp + t0;
-            const T *feed = sm.pring + s0 * LP, *stat = sm.qring + s0 * LP;
-            T *dst_feed = BETA ? a.ctx.fcc_w : st;                               // beta: the feed ring is u o Q, qring the state
-            if (LP == lpi) {
-                bulk_s2g(dst_feed + grow * lpi, feed, (unsigned)(sizeof(T) * rows * lpi));
-                if (BETA) bulk_s2g(st + grow * lpi, stat, (unsigned)(sizeof(T) * rows * lpi));
-            } else {
-                for (int r = 0; r < rows; ++r) {
-                    bulk_s2g(dst_feed + (grow + r) * lpi, feed + r * LP, (unsigned)(sizeof(T) * lpi));
-                    if (BETA) bulk_s2g(st + (grow + r) * lpi, stat + r * LP, (unsigned)(sizeof(T) * lpi));
-                }
+    if (a.ctx.rec != nullptr) {
+        const int s0 = (g % PRG) * FB + (BETA ? FB - rows : 0);           // first ring slot of the run (ascending frames)
+        const int t0 = BETA ? (Tn - g * FB - rows) : g * FB;                // first frame of the run
+        const int64_t grow = (int64_t)n * a.ctx.tp + t0;
+        constexpr int VPR = (int)(LP * sizeof(T) / 16);                     // 16-byte vectors per row
+        const int o_feed = BETA ? a.ctx.o_cw : a.ctx.o_ca;                  // beta: the feed ring is u o Q, qring the state
+        for (int idx = lane; idx < rows * VPR; idx += 32) {
+            const int r = idx / VPR, v = idx - r * VPR;
+            char *rec = a.ctx.record(grow + r);
+            const uint4 f = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(sm.pring + (s0 + r) * LP) + 16 * v);
+            __stcs(reinterpret_cast<uint4 *>(rec + o_feed + 16 * v), f);
+            if (BETA) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(sm.qring + (s0 + r) * LP) + 16 * v);
+                __stcs(reinterpret_cast<uint4 *>(rec + a.ctx.o_cb + 16 * v), q);
             }
-            if (!BETA) bulk_s2g(a.ctx.fcc_scale + grow, sm.scring + s0, (unsigned)(sizeof(T) * ((rows + 3) / 4 * 4)));
         }
-        bulk_commit();
-        // all but the newest group have been read out of shared memory: their slots are free again
-        if (g * FB + rows >= Tn) { bulk_wait_all<0>(); st_volatile_s32(&sm.flushed, g + 1); }
-        else { bulk_wait_read<1>(); st_volatile_s32(&sm.flushed, g); }
+        if (!BETA)
+            for (int r = lane; r < rows; r += 32) *a.ctx.fcc_scale(grow + r) = sm.scring[s0 + r];
     }
+    __syncwarp();
+    if (lane == 0) st_volatile_s32(&sm.flushed, g + 1);                     // the rows are in registers / on their way: slots free
 }
 
 template <typename T, int LP>
@@ -609,13 +606,13 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
     constexpr int KNB = 64;                     // a block never sits more than 2^KNB below the neighbour that feeds it
 
     // state rows of this utterance are contiguous: walk them with pointers
+    // this utterance's frame records are contiguous: walk them with pointers (record stride)
     const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
-    T *stp = BETA ? a.fac_beta : a.fac_alpha;
-    const bool store = owns && stp != nullptr;
-    int *esp = (BETA ? a.ctx.fac_eb : a.ctx.fac_ea) + row0 * nbp + gl;
-    if (stp) stp += row0 * sp + s0;
-    const int64_t sstep = BETA ? -(int64_t)sp : (int64_t)sp;
-    const int64_t estep = BETA ? -(int64_t)nbp : (int64_t)nbp;
+    const bool store = owns && a.ctx.rec != nullptr;
+    T *stp = (BETA ? a.ctx.fac_beta(row0) : a.ctx.fac_alpha(row0)) + s0;
+    int *esp = (BETA ? a.ctx.fac_eb(row0) : a.ctx.fac_ea(row0)) + gl;
+    const int64_t sstep = (BETA ? -a.ctx.R : a.ctx.R) / (int64_t)sizeof(T);
+    const int64_t estep = (BETA ? -a.ctx.R : a.ctx.R) / (int64_t)sizeof(int);
     const bool store_e = store && gl < nblk;
 
     T v[ASG_BLK];        // alpha: P ; beta: Q (mantissas)
@@ -767,12 +764,11 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
     constexpr int KNB = 64;
 
     const int64_t row0 = (int64_t)n * tp + (BETA ? Tn - 1 : 0);
-    T *stp = BETA ? a.fac_beta : a.fac_alpha;
-    const bool store = owns && stp != nullptr;
-    int *esp = (BETA ? a.ctx.fac_eb : a.ctx.fac_ea) + row0 * nbp + lane;
-    if (stp) stp += row0 * sp + s0;
-    const int64_t sstep = BETA ? -(int64_t)sp : (int64_t)sp;
-    const int64_t estep = BETA ? -(int64_t)nbp : (int64_t)nbp;
+    const bool store = owns && a.ctx.rec != nullptr;
+    T *stp = (BETA ? a.ctx.fac_beta(row0) : a.ctx.fac_alpha(row0)) + s0;
+    int *esp = (BETA ? a.ctx.fac_eb(row0) : a.ctx.fac_ea(row0)) + lane;
+    const int64_t sstep = (BETA ? -a.ctx.R : a.ctx.R) / (int64_t)sizeof(T);
+    const int64_t estep = (BETA ? -a.ctx.R : a.ctx.R) / (int64_t)sizeof(int);
     const bool store_e = store && lane < nblk;
     const float edge_mask = BETA ? (lane == 31 ? 0.f : 1.f) : (lane == 0 ? 0.f : 1.f);
 

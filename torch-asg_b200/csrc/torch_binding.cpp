@@ -6,10 +6,10 @@
 // What the returned "alpha / beta / gamma / path_contrib" tensors hold differs from the reference by design
 // (asg.py only looks at alpha.shape / full_gamma.shape -- asg.py:28,50,88 -- and hands everything else
 // straight back to our own backward):
-//   alpha / full_gamma         scaled real-domain FCC alpha: a [T,N,L] view of an utterance-major [N,tp,lpi] buffer
-//   aligned alpha / gamma      block-floating-point FAC alpha: a [T,N,S] view of an utterance-major [N,tp,sp] buffer
-//   beta                       the matching beta state
-//   path_contrib               an opaque uint8 context blob (asg_layout_t) -- NOT a [T-1,N,L,L] tensor
+//   alpha / full_gamma         scaled real-domain FCC alpha: a [T,N,L] strided view into the frame-record array
+//   aligned alpha / gamma      block-floating-point FAC alpha: a [T,N,S] strided view into the same array
+//   beta                       the matching beta part of the records
+//   path_contrib               opaque uint8 blobs (the context blob / the frame-record array, asg_layout_t) -- NOT [T-1,N,L,L]
 // There is no CPU path: CPU tensors raise.
 #include <torch/extension.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -53,10 +53,18 @@ Tensor bytes_like(const Tensor &like, size_t nbytes) {
     return at::empty({(int64_t)nbytes}, like.options().dtype(at::kByte).requires_grad(false));
 }
 
-// [T,N,W] view (what asg.py inspects the shape of) of an utterance-major [N,tp,pitch] state buffer
-Tensor state_view(const Tensor &buf, int64_t T, int64_t W) { return buf.narrow(1, 0, T).narrow(2, 0, W).permute({1, 0, 2}); }
-bool is_state_view(const Tensor &v, int64_t tp, int64_t pitch) {
-    return v.dim() == 3 && v.stride(2) == 1 && v.stride(0) == pitch && v.stride(1) == tp * pitch && v.storage_offset() == 0;
+// [T,N,W] view (what asg.py inspects the shape of) of one part of the frame records held by the byte tensor `state`
+Tensor rec_view(const Tensor &state, const asg_layout_t &lay, size_t part, at::ScalarType dt, int64_t T, int64_t N, int64_t W) {
+    const int64_t eb = (int64_t)lay.elem_bytes, rs = (int64_t)lay.rec_bytes / eb;
+    return state.view(dt).as_strided({T, N, W}, {rs, lay.tp * rs, 1}, (int64_t)part / eb);
+}
+// the base of the frame-record array a view produced by rec_view() points into (or raises)
+void *rec_base(const Tensor &v, const asg_layout_t &lay, size_t part, const char *what) {
+    const int64_t eb = (int64_t)lay.elem_bytes, rs = (int64_t)lay.rec_bytes / eb;
+    TORCH_CHECK(v.dim() == 3 && v.stride(2) == 1 && v.stride(0) == rs && v.stride(1) == lay.tp * rs &&
+                    v.storage_offset() == (int64_t)part / eb && (size_t)v.storage().nbytes() >= lay.state_bytes,
+                what, " is not a state tensor produced by this extension's forward");
+    return static_cast<char *>(v.data_ptr()) - part;
 }
 
 void check_inputs(const Tensor &inputs, const Tensor &transition, int64_t T, int64_t N, int64_t L) {
@@ -81,13 +89,15 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> fully_connected_forward(Tensor &input
     Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
     const asg_layout_t lay = layout_of(dt, T, N, L, 1);
     auto opt = inputs.options().requires_grad(false);
-    Tensor alpha = at::empty({N, lay.tp, lay.lpi}, opt), beta = at::empty({N, lay.tp, lay.lpi}, opt), scores = at::empty({N}, opt);
+    Tensor scores = at::empty({N}, opt);
+    Tensor state = bytes_like(inputs, lay.state_bytes);
     Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
     check_rc(asg_scan(dt, ASG_ROLE_FCC_ALPHA | ASG_ROLE_FCC_BETA, inputs.data_ptr(), inputs.stride(0), inputs.stride(1),
                       inputs.stride(2), transition.data_ptr(), transition.stride(0), transition.stride(1), nullptr, 0, 0,
-                      il.data_ptr<int64_t>(), nullptr, T, N, L, 1, alpha.data_ptr(), beta.data_ptr(), nullptr, nullptr,
-                      ctx.data_ptr(), scores.data_ptr(), nullptr, current_stream()));
-    return {scores, state_view(alpha, T, L), state_view(beta, T, L), ctx};
+                      il.data_ptr<int64_t>(), nullptr, T, N, L, 1, state.data_ptr(), ctx.data_ptr(), scores.data_ptr(), nullptr,
+                      current_stream()));
+    const auto st = inputs.scalar_type();
+    return {scores, rec_view(state, lay, lay.rec_fcc_alpha, st, T, N, L), rec_view(state, lay, lay.rec_fcc_beta, st, T, N, L), ctx};
 }
 
 // reference: fully_connected_backward, fully_connected_lattice.h:51-60 / .cpp:94-104
@@ -99,15 +109,13 @@ std::tuple<Tensor, Tensor> fully_connected_backward(Tensor &grad_out, Tensor &al
     const asg_layout_t lay = layout_of(dt, T, N, L, 1);
     TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
                 "path_contrib is not a context blob produced by this extension's fully_connected_forward");
-    TORCH_CHECK(is_state_view(alpha, lay.tp, lay.lpi) && is_state_view(beta, lay.tp, lay.lpi),
-                "alpha/beta are not the state tensors produced by this extension's fully_connected_forward");
+    void *state = rec_base(alpha, lay, lay.rec_fcc_alpha, "alpha");
     Tensor g = grad_out.to(alpha.options());
     auto opt = alpha.options().requires_grad(false);
     Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
     Tensor scratch = bytes_like(alpha, lay.grad_scratch_bytes);
-    check_rc(asg_grad(dt, ASG_PART_FCC, g.data_ptr(), g.dim() ? g.stride(0) : 0, nullptr, 0, alpha.data_ptr(), beta.data_ptr(),
-                      nullptr, nullptr, path_contrib.data_ptr(), nullptr, 0, 0, T, N, L, 1, grad_x.data_ptr(), grad_A.data_ptr(),
-                      scratch.data_ptr(), current_stream()));
+    check_rc(asg_grad(dt, ASG_PART_FCC, g.data_ptr(), g.dim() ? g.stride(0) : 0, nullptr, 0, state, path_contrib.data_ptr(),
+                      nullptr, 0, 0, T, N, L, 1, grad_x.data_ptr(), grad_A.data_ptr(), scratch.data_ptr(), current_stream()));
     return {grad_A, grad_x};
 }
 
@@ -124,14 +132,15 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> force_aligned_forward(Tensor &inputs,
     TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
-    Tensor alpha = at::empty({N, lay.tp, lay.sp}, opt), beta = at::empty({N, lay.tp, lay.sp}, opt), scores = at::empty({N}, opt);
+    Tensor scores = at::empty({N}, opt);
+    Tensor state = bytes_like(inputs, lay.state_bytes);
     Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
     check_rc(asg_scan(dt, ASG_ROLE_FAC_ALPHA | ASG_ROLE_FAC_BETA, inputs.data_ptr(), inputs.stride(0), inputs.stride(1),
                       inputs.stride(2), transition.data_ptr(), transition.stride(0), transition.stride(1),
                       y.data_ptr<int64_t>(), y.stride(0), y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L,
-                      S, nullptr, nullptr, alpha.data_ptr(), beta.data_ptr(), ctx.data_ptr(), nullptr, scores.data_ptr(),
-                      current_stream()));
-    return {scores, state_view(alpha, T, S), state_view(beta, T, S), ctx};
+                      S, state.data_ptr(), ctx.data_ptr(), nullptr, scores.data_ptr(), current_stream()));
+    const auto st = inputs.scalar_type();
+    return {scores, rec_view(state, lay, lay.rec_fac_alpha, st, T, N, S), rec_view(state, lay, lay.rec_fac_beta, st, T, N, S), ctx};
 }
 
 // reference: force_aligned_backward, force_aligned_lattice.h:56-69 / .cpp:321-356
@@ -144,16 +153,15 @@ std::tuple<Tensor, Tensor> force_aligned_backward(Tensor &grad_out, Tensor &alph
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
                 "path_contrib is not a context blob produced by this extension's force_aligned_forward");
-    TORCH_CHECK(is_state_view(alpha, lay.tp, lay.sp) && is_state_view(beta, lay.tp, lay.sp),
-                "alpha/beta are not the state tensors produced by this extension's force_aligned_forward");
+    void *state = rec_base(alpha, lay, lay.rec_fac_alpha, "alpha");
     Tensor y = as_device_long(targets, alpha, "targets");
     Tensor g = grad_out.to(alpha.options());
     auto opt = alpha.options().requires_grad(false);
     Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
     Tensor scratch = bytes_like(alpha, lay.grad_scratch_bytes);
-    check_rc(asg_grad(dt, ASG_PART_FAC, nullptr, 0, g.data_ptr(), g.dim() ? g.stride(0) : 0, nullptr, nullptr, alpha.data_ptr(),
-                      beta.data_ptr(), path_contrib.data_ptr(), y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S,
-                      grad_x.data_ptr(), grad_A.data_ptr(), scratch.data_ptr(), current_stream()));
+    check_rc(asg_grad(dt, ASG_PART_FAC, nullptr, 0, g.data_ptr(), g.dim() ? g.stride(0) : 0, state, path_contrib.data_ptr(),
+                      y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S, grad_x.data_ptr(), grad_A.data_ptr(),
+                      scratch.data_ptr(), current_stream()));
     return {grad_A, grad_x};
 }
 
@@ -169,13 +177,12 @@ Tensor fast_asg_gpu_forward_only(Tensor &inputs, Tensor &targets, Tensor &transi
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
     Tensor full = at::empty({N}, opt), aligned = at::empty({N}, opt);
-    // forward-only keeps no state: only the small head of the context blob (E, lengths, scalars) is touched,
-    // but the offsets are those of the full layout, so the blob is allocated whole (uninitialised, untouched).
+    // forward-only keeps no state: no frame records, only the small context blob (E, lengths, scalars)
     Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
     check_rc(asg_scan(dt, ASG_ROLE_FORWARD_ONLY, inputs.data_ptr(), inputs.stride(0), inputs.stride(1), inputs.stride(2),
                       transition.data_ptr(), transition.stride(0), transition.stride(1), y.data_ptr<int64_t>(), y.stride(0),
-                      y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, nullptr, nullptr, nullptr,
-                      nullptr, ctx.data_ptr(), full.data_ptr(), aligned.data_ptr(), current_stream()));
+                      y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, nullptr, ctx.data_ptr(),
+                      full.data_ptr(), aligned.data_ptr(), current_stream()));
     return full - aligned;
 }
 
@@ -194,18 +201,15 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fast_asg_gpu_forward(
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
     Tensor full = at::empty({N}, opt), aligned = at::empty({N}, opt);
-    Tensor fcc_alpha = at::empty({N, lay.tp, lay.lpi}, opt);
-    Tensor fac_alpha = at::empty({N, lay.tp, lay.sp}, opt);
-    // the two beta states travel in one opaque tensor (the "aligned_path_contrib" slot)
-    const size_t fb = (lay.fcc_state_bytes + 255) / 256 * 256;
-    Tensor betas = bytes_like(inputs, fb + lay.fac_state_bytes);
+    // the frame records travel in the "aligned_path_contrib" slot, the context blob in "full_path_contrib"
+    Tensor state = bytes_like(inputs, lay.state_bytes);
     Tensor ctx = bytes_like(inputs, lay.ctx_bytes);
-    char *bp = static_cast<char *>(betas.data_ptr());
     check_rc(asg_scan(dt, ASG_ROLE_ALL, inputs.data_ptr(), inputs.stride(0), inputs.stride(1), inputs.stride(2),
                       transition.data_ptr(), transition.stride(0), transition.stride(1), y.data_ptr<int64_t>(), y.stride(0),
-                      y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, fcc_alpha.data_ptr(), bp,
-                      fac_alpha.data_ptr(), bp + fb, ctx.data_ptr(), full.data_ptr(), aligned.data_ptr(), current_stream()));
-    return {full, aligned, state_view(fcc_alpha, T, L), state_view(fac_alpha, T, S), ctx, betas};
+                      y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S, state.data_ptr(), ctx.data_ptr(),
+                      full.data_ptr(), aligned.data_ptr(), current_stream()));
+    const auto st = inputs.scalar_type();
+    return {full, aligned, rec_view(state, lay, lay.rec_fcc_alpha, st, T, N, L), rec_view(state, lay, lay.rec_fac_alpha, st, T, N, S), ctx, state};
 }
 
 // reference: fast_asg_gpu_backward, streamlined_fast_gpu.h:50-68 / .cpp:236-297
@@ -217,21 +221,20 @@ std::tuple<Tensor, Tensor> fast_asg_gpu_backward(Tensor &grad_full, Tensor &grad
     c10::cuda::CUDAGuard guard(full_gamma.device());
     const int dt = dtype_code(full_gamma, "full_gamma");
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
-    const size_t fb = (lay.fcc_state_bytes + 255) / 256 * 256;
     TORCH_CHECK((size_t)full_path_contrib.numel() == lay.ctx_bytes && full_path_contrib.scalar_type() == at::kByte &&
-                    (size_t)aligned_path_contrib.numel() == fb + lay.fac_state_bytes &&
-                    is_state_view(aligned_gamma, lay.tp, lay.sp) && is_state_view(full_gamma, lay.tp, lay.lpi),
+                    (size_t)aligned_path_contrib.numel() == lay.state_bytes && aligned_path_contrib.scalar_type() == at::kByte,
                 "saved tensors were not produced by this extension's fast_asg_gpu_forward");
+    TORCH_CHECK(rec_base(full_gamma, lay, lay.rec_fcc_alpha, "full_gamma") == aligned_path_contrib.data_ptr() &&
+                    rec_base(aligned_gamma, lay, lay.rec_fac_alpha, "aligned_gamma") == aligned_path_contrib.data_ptr(),
+                "saved tensors were not produced by the same fast_asg_gpu_forward call");
     Tensor y = as_device_long(targets, full_gamma, "targets");
     Tensor gf = grad_full.to(full_gamma.options()), ga = grad_aligned.to(full_gamma.options());
     auto opt = full_gamma.options().requires_grad(false);
     Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
     Tensor scratch = bytes_like(full_gamma, lay.grad_scratch_bytes);
-    char *bp = static_cast<char *>(aligned_path_contrib.data_ptr());
     check_rc(asg_grad(dt, ASG_PART_BOTH, gf.data_ptr(), gf.dim() ? gf.stride(0) : 0, ga.data_ptr(), ga.dim() ? ga.stride(0) : 0,
-                      full_gamma.data_ptr(), bp, aligned_gamma.data_ptr(), bp + fb, full_path_contrib.data_ptr(),
-                      y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S, grad_x.data_ptr(), grad_A.data_ptr(),
-                      scratch.data_ptr(), current_stream()));
+                      aligned_path_contrib.data_ptr(), full_path_contrib.data_ptr(), y.data_ptr<int64_t>(), y.stride(0), y.stride(1),
+                      T, N, L, S, grad_x.data_ptr(), grad_A.data_ptr(), scratch.data_ptr(), current_stream()));
     return {grad_A, grad_x};
 }
 
