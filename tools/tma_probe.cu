@@ -59,6 +59,39 @@ __global__ void ldg_stream(const float4 *src, size_t n4_per_cta, float *sink) {
     if (acc == 123.456f) sink[0] = acc;
 }
 
+// the gradient kernel's protocol: one producer warp + NW consumer warps, full/empty mbarrier pairs, chunks of `csize`
+// bytes advancing by `adv` bytes (overlapping halo), consumers touch one word and release
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__global__ void ring_stream(const char *src, size_t bytes_per_cta, int csize, int adv, int depth, int nw, float *sink) {
+    extern __shared__ __align__(128) char smem[];
+    __shared__ uint64_t full[16], empty[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { for (int i = 0; i < depth; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], nw); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const char *base = src + (size_t)blockIdx.x * bytes_per_cta;
+    const int nchunks = (int)((bytes_per_cta - csize) / adv);
+    const size_t sstride = ((size_t)csize + 127) / 128 * 128;
+    float acc = 0.f;
+    if (warp == nw) {
+        if (lane == 0)
+            for (int i = 0; i < nchunks; ++i) {
+                const int s = i % depth, use = i / depth;
+                mbar_wait(&empty[s], (use & 1) ^ 1);
+                mbar_expect(&full[s], (unsigned)csize);
+                bulk(smem + s * sstride, base + (size_t)i * adv, (unsigned)csize, &full[s]);
+            }
+    } else {
+        for (int i = 0; i < nchunks; ++i) {
+            const int s = i % depth, use = i / depth;
+            mbar_wait(&full[s], use & 1);
+            acc += *(float *)(smem + s * sstride + (warp * 32 + lane) * 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
 int main() {
     const size_t total = (size_t)592 << 20;   // 592 MiB > L2
     char *src; float *sink;
@@ -77,9 +110,9 @@ int main() {
     cudaEventElapsedTime(&ms, e0, e1);
     printf("ldg.128 x4 unroll, 296x512 thr:  %.0f GB/s\n", per * sms / ms / 1e6);
     cudaFuncSetAttribute(tma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const int sizes[] = {2048, 8192, 16384, 32768};
-    const int depths[] = {1, 2, 4, 6, 12};
-    const int splits[] = {1, 8};
+    const int sizes[] = {32768};
+    const int depths[] = {1, 4};
+    const int splits[] = {1};
     for (int split : splits)
         for (int cs : sizes)
             for (int d : depths) {
@@ -92,5 +125,20 @@ int main() {
                 printf("bulk copy %6d B x depth %2d x split %d (in flight %6d B/SM): %6.0f GB/s  %s\n", cs, d, split, cs * d, per * sms / ms / 1e6,
                        cudaGetLastError() == cudaSuccess ? "" : "ERR");
             }
+    cudaFuncSetAttribute(ring_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int rec = 2368;
+    const int cfgs[][4] = {{13 * rec, 12 * rec, 5, 17}, {13 * rec, 12 * rec, 5, 1}, {13 * rec, 13 * rec, 5, 17}, {32768, 32768, 5, 17}, {32768, 32768, 5, 1},
+                           {17 * rec, 16 * rec, 4, 17}, {25 * rec, 24 * rec, 3, 17}};
+    for (auto &c : cfgs) {
+        const size_t smem = ((size_t)c[0] + 127) / 128 * 128 * c[2];
+        ring_stream<<<sms, 32 * (c[3] + 1), smem>>>(src, per, c[0], c[1], c[2], c[3], sink);
+        cudaEventRecord(e0);
+        ring_stream<<<sms, 32 * (c[3] + 1), smem>>>(src, per, c[0], c[1], c[2], c[3], sink);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const size_t nch = (per - c[0]) / c[1];
+        printf("ring: chunk %6d B advance %6d B depth %d consumers %2d warps: %6.0f GB/s moved (%6.0f GB/s useful)  %s\n", c[0], c[1], c[2], c[3],
+               (double)nch * c[0] * sms / ms / 1e6, (double)nch * c[1] * sms / ms / 1e6, cudaGetLastError() == cudaSuccess ? "" : cudaGetErrorString(cudaGetLastError()));
+    }
     return 0;
 }

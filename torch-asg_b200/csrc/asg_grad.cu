@@ -31,6 +31,7 @@
 
 namespace asg {
 
+constexpr int GRAD_MAX_CWARPS = 8;     // consumer warps (+ one producer warp)
 constexpr int GRAD_LBINS = 72;         // label bins per warp: L <= 64, bin L = trash (padding positions)
 
 // Fixed-point images (integers add in any order with the same result, so shared-memory atomics stay deterministic):
@@ -85,7 +86,7 @@ __host__ __device__ inline GradMap grad_map(size_t eb, size_t rec_bytes, int L, 
     m.o_Gal = take(eb * (size_t)L * L);
     m.o_Gf = take(fcc ? eb * (size_t)L * L : 0);
     m.o_galfix = take(fac ? 8 * 2 * (size_t)L * L : 0);
-    m.o_bins = take(fac ? 8 * (size_t)nw * GRAD_LBINS : 0);
+    m.o_bins = take(fac ? 8 * (size_t)nw * 2 * GRAD_LBINS : 0);
     m.o_acc = take((fac && sp > 256) ? eb * (size_t)nw * 2 * sp : 0);
     m.o_bars = take(sizeof(uint64_t) * 3 * 8);
     m.o_stages = align_up(off, 128);
@@ -107,32 +108,23 @@ __device__ __forceinline__ void lds8(const double *p, double (&v)[8]) {
     }
 }
 
-// warp roles per CTA: NF frame warps (one frame of the tile each), NO outer-product warps (8 rows of G each, FCC
-// only), one producer warp.  Registers are allocated per kernel, so splitting the roles keeps every thread under
-// ~112 registers and lets 18 warps share an SM instead of 9.
-template <int LP> __host__ __device__ constexpr int grad_frame_warps() { return LP <= 40 ? 12 : 8; }
-template <int LP, bool FCC> __host__ __device__ constexpr int grad_outer_warps() { return FCC ? LP / 8 : 0; }
-template <int LP, bool FCC> __host__ __device__ constexpr int grad_threads() { return 32 * (grad_frame_warps<LP>() + grad_outer_warps<LP, FCC>() + 1); }
-
 template <typename T, int LP, bool FCC, bool FAC>
-__global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const GradArgs<T> a) {
+__global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(const GradArgs<T> a) {
     extern __shared__ __align__(128) char smem_raw[];
     typedef typename Fix<T>::bin_t bin_t;
-    typedef Fix<T> FX;
-    constexpr int NF = grad_frame_warps<LP>(), NO = grad_outer_warps<LP, FCC>();
     const int L = a.d.L, N = a.d.N, Tt = a.d.T;
     const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp, lpi = (int)a.ctx.lpi;
     const int64_t tp = a.ctx.tp;
-    const int TB = a.tb, NS = a.nstage;
-    const GradMap mp = grad_map(sizeof(T), (size_t)a.ctx.R, L, sp, TB, NS, NF, FCC, FAC);
+    const int TB = a.tb, NS = a.nstage, NW = a.nwarps;
+    const GradMap mp = grad_map(sizeof(T), (size_t)a.ctx.R, L, sp, TB, NS, NW, FCC, FAC);
     const int R = (int)a.ctx.R;                    // frame record size in bytes
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nframe = NF * 32;                    // threads of the frame warps (named barrier 1)
+    const int ncons = NW * 32;
 
     T *hh = (T *)(smem_raw + mp.o_hh), *din = (T *)(smem_raw + mp.o_din);
-    T *Gal = (T *)(smem_raw + mp.o_Gal);
+    T *Gal = (T *)(smem_raw + mp.o_Gal), *Gf = (T *)(smem_raw + mp.o_Gf);
     int *ylab = (int *)(smem_raw + mp.o_ylab);
-    uint64_t *full = (uint64_t *)(smem_raw + mp.o_bars), *mid = full + 8, *empty = full + 16;
+    uint64_t *full = (uint64_t *)(smem_raw + mp.o_bars), *empty = full + 8;
     char *stages = smem_raw + mp.o_stages;
 
     // balanced contiguous tile ranges
@@ -140,14 +132,14 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
     const int q_end = (int)(((int64_t)a.num_tiles * (blockIdx.x + 1)) / gridDim.x);
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&mid[s], NF); mbar_init(&empty[s], NF + NO); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
         mbar_fence_init();
     }
     __syncthreads();
 
     // =========================== producer warp: ONE bulk copy per tile ================================
     // records t0-1 .. t0+rows-1 of the utterance are one contiguous chunk of the state array
-    if (warp == NF + NO) {
+    if (warp == NW) {
         if (lane == 0) {
             int n = q_begin / a.tiles_t, tt = q_begin - n * a.tiles_t;     // walked, no per-tile divisions
             int Tn = (q_begin < q_end) ? (int)a.ctx.il[n] : 0;
@@ -174,67 +166,27 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
         return;
     }
 
-    // =========================== outer-product warps: G += (w_t * winv_t) (x) alpha_{t-1} ==========================
-    // warp o owns rows 8o .. 8o+7 of G for every frame this CTA sees; lane l owns columns l and l+32.  No other warp
-    // touches these elements, so there is nothing to reduce at the end.
-    if (FCC && warp >= NF) {
-        const int o = warp - NF;
-        T G0[8], G1[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) G0[i] = G1[i] = T(0);
-        const bool c0 = lane < lpi, c1 = (LP > 32) && (lane + 32 < lpi);
-        int cur_n = -1, Tn = 0;
-        int it = 0;
-        for (int q = q_begin; q < q_end; ++q, ++it) {
-            const int stage = it % NS, use = it / NS;
-            const int n = q / a.tiles_t;
-            const int t0 = (q % a.tiles_t) * TB;
-            const int TBt = min(TB, Tt - t0);
-            if (n != cur_n) { cur_n = n; Tn = (int)a.ctx.il[n]; }
-            const int rows_valid = max(0, min(TBt, Tn - t0));
-            char *sb = stages + (size_t)stage * mp.stage_bytes;
-            const char *srec = sb + mp.oRec;
-            const T *sWi = (const T *)(sb + mp.oWinv);
-            mbar_wait(&full[stage], use & 1);
-            mbar_wait(&mid[stage], use & 1);                       // every frame warp has published its winv
-            for (int r = (t0 > 0 ? 1 : 2); r <= rows_valid && !a.dry; ++r) {   // frame 0 has no incoming edge
-                const T winv = sWi[r - 1];
-                T wv[8];
-                lds8((const T *)(srec + (size_t)r * R + a.ctx.o_cw) + o * 8, wv);                 // u o beta of frame t
-                const T *pa = (const T *)(srec + (size_t)(r - 1) * R + a.ctx.o_ca);                 // alpha of frame t-1
-                const T p0 = c0 ? pa[lane] * winv : T(0);
-                const T p1 = c1 ? pa[lane + 32] * winv : T(0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { G0[i] = fma(wv[i], p0, G0[i]); if (LP > 32) G1[i] = fma(wv[i], p1, G1[i]); }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-        }
-        // hand the slice over: Gf[i][j] is written by exactly one lane
-        T *Gf = (T *)(smem_raw + mp.o_Gf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int gi = o * 8 + i;
-            if (gi < L) {
-                if (lane < L) Gf[gi * L + lane] = G0[i];
-                if (LP > 32 && lane + 32 < L) Gf[gi * L + lane + 32] = G1[i];
-            }
-        }
-        named_bar_sync(2, (NF + NO) * 32);                         // meets the frame warps before the partial is written
-        return;
-    }
-
-    // =========================== frame warps ========================================================
-    auto cbar = [&]() { named_bar_sync(1, nframe); };
+    // =========================== consumer warps =====================================================
+    auto cbar = [&]() { named_bar_sync(1, ncons); };
     const bool narrow = nblk <= 32;                // one 8-position block per lane: everything stays in registers
+    typedef Fix<T> FX;
+
+    // FCC: per-lane register slice of this warp's G: rows ib*RI.., columns jb*CJ..
+    constexpr int RI = LP / 8, CJ = LP / 4;
+    const int ib = lane >> 2, jb = lane & 3;
+    T G[RI][CJ];
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) G[i][j] = T(0);
 
     unsigned long long *galfix = (unsigned long long *)(smem_raw + mp.o_galfix);     // [2][L*L] fixed-point edge sums
-    for (int e = tid; e < L * L; e += nframe) { Gal[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
+    for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
 
-    bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * GRAD_LBINS;
+    bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * 2 * GRAD_LBINS;     // two sets: one per frame in flight
     T *acc = (T *)(smem_raw + mp.o_acc) + (size_t)warp * 2 * sp;     // wide mode only: [2][sp] stay / total sums of this warp
     if (FAC) {
-        for (int l = lane; l < GRAD_LBINS; l += 32) bins[l] = 0;
+        for (int l = lane; l < 2 * GRAD_LBINS; l += 32) bins[l] = 0;
         if (!narrow)
             for (int s = lane; s < 2 * sp; s += 32) acc[s] = T(0);
     }
@@ -277,7 +229,7 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
             }
         }
         cbar();
-        for (int e = tid; e < L * L; e += nframe) {
+        for (int e = tid; e < L * L; e += ncons) {
             Gal[e] += ga * FX::edge_unfix(gfix[e]);
             gfix[e] = 0;
         }
@@ -314,7 +266,7 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     labm1 = __shfl_up_sync(ASG_FULL_MASK, lab[7], 1);
                 } else {
                     cbar();                        // the previous utterance's frames are done everywhere
-                    for (int s = tid; s < sp; s += nframe) {
+                    for (int s = tid; s < sp; s += ncons) {
                         int lb = L;
                         if (s < Sn) lb = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
                         ylab[s] = lb;
@@ -327,40 +279,152 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
         }
         const int rows_valid = max(0, min(TBt, Tn - t0));   // frames t0 .. t0+rows_valid-1 are inside the utterance
         char *sb = stages + (size_t)stage * mp.stage_bytes;
+        // record r of the stage = frame t0-1+r (r = 0 is the halo); every part of a frame sits in its own record
         const char *srec = sb + mp.oRec;
-        T *sWi = (T *)(sb + mp.oWinv);
+        auto A_ = [&](int r) { return (const T *)(srec + (size_t)r * R + a.ctx.o_fa); };
+        auto B_ = [&](int r) { return (const T *)(srec + (size_t)r * R + a.ctx.o_fb); };
+        auto Ea_ = [&](int r) { return (const int *)(srec + (size_t)r * R + a.ctx.o_ea); };
+        auto Eb_ = [&](int r) { return (const int *)(srec + (size_t)r * R + a.ctx.o_eb); };
+        auto Fa_ = [&](int r) { return (const T *)(srec + (size_t)r * R + a.ctx.o_ca); };
+        auto Fb_ = [&](int r) { return (const T *)(srec + (size_t)r * R + a.ctx.o_cb); };
+        auto Fw_ = [&](int r) { return (const T *)(srec + (size_t)r * R + a.ctx.o_cw); };
+        auto Sc_ = [&](int r) { return *(const T *)(srec + (size_t)r * R + a.ctx.o_sc); };
 
         mbar_wait(&full[stage], use & 1);
 
         // smem row r of the alpha arrays = frame t0-1+r (r = 0 is the halo); beta arrays: row r-1 = frame t0-1+r
-        bool arrived_mid = false;
-        for (int r = 1 + warp; r <= TBt; r += NF) {
+        // ---- fast path: both of this warp's frames are live interior frames -> do them together, so that the two
+        //      independent dependency chains (loads, REDUX, shuffle trees, divisions) overlap in one instruction stream
+        if (narrow && TB == 2 * NW && rows_valid == TB && t0 > 0 && !a.dry) {
+            const int ra = 1 + warp, rb = 1 + warp + NW;
+            const int rr[2] = {ra, rb};
+            const int lb8 = min(lane, nblk - 1) * 8;          // idle lanes re-read the last block (weight 0)
+            const int le = min(lane, nblk - 1);
+            const bool act = lane < nblk;
+            T bv[2][8];
+            if (FAC) {
+                T av[2][8];
+                int ea[2], eb[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    lds8(A_(rr[u]) + lb8, av[u]);
+                    lds8(B_(rr[u]) + lb8, bv[u]);
+                    ea[u] = Ea_(rr[u])[le];
+                    eb[u] = Eb_(rr[u])[le];
+                }
+                T pv[2][8];
+                int ep[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    lds8(A_(rr[u] - 1) + lb8, pv[u]);
+                    ep[u] = Ea_(rr[u] - 1)[le];
+                }
+                T ps[2];
+                int c[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bv[u][j] = av[u][j] * (bv[u][j] * Num<T>::prod_scale());
+                    const T pm = tmax(tmax(tmax(bv[u][0], bv[u][1]), tmax(bv[u][2], bv[u][3])), tmax(tmax(bv[u][4], bv[u][5]), tmax(bv[u][6], bv[u][7])));
+                    ps[u] = ((bv[u][0] + bv[u][1]) + (bv[u][2] + bv[u][3])) + ((bv[u][4] + bv[u][5]) + (bv[u][6] + bv[u][7]));
+                    c[u] = (act && pm > T(0)) ? ea[u] + eb[u] : INT_MIN;
+                }
+                const int cmax0 = __reduce_max_sync(ASG_FULL_MASK, c[0]);
+                const int cmax1 = __reduce_max_sync(ASG_FULL_MASK, c[1]);
+                T wgt[2];
+                wgt[0] = (c[0] != INT_MIN && c[0] - cmax0 >= -Num<T>::kMaxShift) ? Num<T>::exp2i(c[0] - cmax0) : T(0);
+                wgt[1] = (c[1] != INT_MIN && c[1] - cmax1 >= -Num<T>::kMaxShift) ? Num<T>::exp2i(c[1] - cmax1) : T(0);
+                T z0 = ps[0] * wgt[0], z1 = ps[1] * wgt[1];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    z0 += __shfl_xor_sync(ASG_FULL_MASK, z0, o);
+                    z1 += __shfl_xor_sync(ASG_FULL_MASK, z1, o);
+                }
+                const T Z[2] = {z0, z1};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const T invZ = (Z[u] > Num<T>::tiny()) ? T(1) / Z[u] : T(0);
+                    const T kq = wgt[u] * FX::kPost;
+                    bin_t *bu = bins + u * GRAD_LBINS;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bv[u][j] = (bv[u][j] * invZ) * kq;
+                        FX::add(&bu[lab[j]], FX::to_fix(bv[u][j]));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    T left = __shfl_up_sync(ASG_FULL_MASK, pv[u][7], 1);
+                    const int el = __shfl_up_sync(ASG_FULL_MASK, ep[u], 1);
+                    left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep[u], Num<T>::kMaxShift - 8));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const T stay = hreg[j] * pv[u][j];
+                        const T den = fma(dreg[j], j ? pv[u][j ? j - 1 : 0] : left, stay);
+                        const T fs = fast_div(stay, tmax(den, Num<T>::tiny()));
+                        accH[j] = fma(bv[u][j], fs, accH[j]);
+                        accQ[j] += bv[u][j];
+                    }
+                }
+                __syncwarp();
+            }
+            T g0[2] = {T(0), T(0)}, g1[2] = {T(0), T(0)};
+            if (FCC) {
+                T inv[2];
+                {
+                    T al0[2], al1[2], be0[2], be1[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        al0[u] = al1[u] = be0[u] = be1[u] = T(0);
+                        if (lane < lpi) { al0[u] = Fa_(rr[u])[lane]; be0[u] = Fb_(rr[u])[lane]; }
+                        if (LP > 32 && lane + 32 < lpi) { al1[u] = Fa_(rr[u])[lane + 32]; be1[u] = Fb_(rr[u])[lane + 32]; }
+                        g0[u] = al0[u] * be0[u]; g1[u] = al1[u] * be1[u];
+                    }
+                    T z0 = g0[0] + g1[0], z1 = g0[1] + g1[1];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        z0 += __shfl_xor_sync(ASG_FULL_MASK, z0, o);
+                        z1 += __shfl_xor_sync(ASG_FULL_MASK, z1, o);
+                    }
+                    inv[0] = (z0 > T(0)) ? gf / z0 : T(0);
+                    inv[1] = (z1 > T(0)) ? gf / z1 : T(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    g0[u] *= inv[u]; g1[u] *= inv[u];
+                    const T winv = inv[u] * Sc_(rr[u]);
+                    T wv[RI], pw[CJ];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) wv[i] = Fw_(rr[u])[ib * RI + i] * winv;
+#pragma unroll
+                    for (int j = 0; j < CJ; ++j) pw[j] = Fa_(rr[u] - 1)[jb * CJ + j];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int j = 0; j < CJ; ++j) G[i][j] = fma(wv[i], pw[j], G[i][j]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                T *gx_row = a.grad_x + ((int64_t)(t0 - 1 + rr[u]) * N + n) * L;
+                T o0 = g0[u], o1 = g1[u];
+                if (FAC) {
+                    bin_t *bu = bins + u * GRAD_LBINS;
+                    const T gs = ga * FX::kInvPost;
+                    if (lane < L) { o0 = fma(gs, FX::from_fix(bu[lane]), o0); bu[lane] = 0; }
+                    if (LP > 32 && lane + 32 < L) { o1 = fma(gs, FX::from_fix(bu[lane + 32]), o1); bu[lane + 32] = 0; }
+                }
+                if (lane < L) gx_row[lane] = o0;
+                if (LP > 32 && lane + 32 < L) gx_row[lane + 32] = o1;
+            }
+            __syncwarp();
+        } else
+        for (int r = 1 + warp; r <= TBt; r += NW) {
             const int t = t0 - 1 + r;
             T *gx_row = a.grad_x + ((int64_t)t * N + n) * L;
             if (r > rows_valid || a.dry) {              // padding frame: exact zeros
                 for (int l = lane; l < L; l += 32) gx_row[l] = T(0);
                 continue;
-            }
-            // ---------------- FCC posterior first: the outer-product warps wait for winv ----------------
-            const char *rec = srec + (size_t)r * R;           // this frame's record; rec - R is frame t-1's
-            const T *sA = (const T *)(rec + a.ctx.o_fa), *sB = (const T *)(rec + a.ctx.o_fb), *sAp = (const T *)(rec - R + a.ctx.o_fa);
-            const int *sEa = (const int *)(rec + a.ctx.o_ea), *sEb = (const int *)(rec + a.ctx.o_eb), *sEp = (const int *)(rec - R + a.ctx.o_ea);
-            T g0 = T(0), g1 = T(0);
-            if (FCC) {
-                const T *sFa = (const T *)(rec + a.ctx.o_ca), *sFb = (const T *)(rec + a.ctx.o_cb);
-                T al0 = T(0), al1 = T(0), be0 = T(0), be1 = T(0);
-                if (lane < lpi) { al0 = sFa[lane]; be0 = sFb[lane]; }
-                if (LP > 32 && lane + 32 < lpi) { al1 = sFa[lane + 32]; be1 = sFb[lane + 32]; }
-                g0 = al0 * be0; g1 = al1 * be1;
-                const T Z = warp_sum(g0 + g1);
-                const T inv = (Z > T(0)) ? gf / Z : T(0);
-                g0 *= inv; g1 *= inv;
-                if (lane == 0) sWi[r - 1] = (t >= 1) ? inv * *(const T *)(rec + a.ctx.o_sc) : T(0);
-            }
-            if (r + NF > TBt) {                         // this warp's last frame of the tile: winv is out
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&mid[stage]);
-                arrived_mid = true;
             }
             // ---------------- FAC: posterior, label scatter, edge posteriors ----------------------
             if (FAC) {
@@ -369,9 +433,9 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     const int le = min(lane, nblk - 1);
                     const bool act = lane < nblk;
                     T av[8], bv[8];
-                    lds8(sA + lb8, av);
-                    lds8(sB + lb8, bv);
-                    const int ea = sEa[le], eb = sEb[le];
+                    lds8(A_(r) + lb8, av);
+                    lds8(B_(r) + lb8, bv);
+                    const int ea = Ea_(r)[le], eb = Eb_(r)[le];
                     // alpha and beta mantissas are normalised separately (block maxima in [1,2)), so where one peaks the
                     // other can be ~2^-100: the products carry a constant 2^120 (2^960) so they stay normal numbers
 #pragma unroll
@@ -392,8 +456,8 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     }
                     if (t >= 1) {
                         T pv[8];
-                        lds8(sAp + lb8, pv);
-                        const int ep = sEp[le];
+                        lds8(A_(r - 1) + lb8, pv);
+                        const int ep = Ea_(r - 1)[le];
                         // the left neighbour's last value, expressed in this block's exponent (bounded so den stays finite)
                         T left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
                         const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
@@ -413,20 +477,20 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     int cmax = INT_MIN;
                     for (int b = lane; b < nblk; b += 32) {
                         T av[8], bv[8];
-                        lds8(sA + b * 8, av);
-                        lds8(sB + b * 8, bv);
+                        lds8(A_(r) + b * 8, av);
+                        lds8(B_(r) + b * 8, bv);
                         T pm = T(0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) pm = tmax(pm, av[j] * (bv[j] * Num<T>::prod_scale()));
-                        if (pm > T(0)) cmax = max(cmax, sEa[b] + sEb[b]);
+                        if (pm > T(0)) cmax = max(cmax, Ea_(r)[b] + Eb_(r)[b]);
                     }
                     cmax = __reduce_max_sync(ASG_FULL_MASK, cmax);
                     T zs = T(0);
                     for (int b = lane; b < nblk; b += 32) {
                         T av[8], bv[8];
-                        lds8(sA + b * 8, av);
-                        lds8(sB + b * 8, bv);
-                        const int c = sEa[b] + sEb[b];
+                        lds8(A_(r) + b * 8, av);
+                        lds8(B_(r) + b * 8, bv);
+                        const int c = Ea_(r)[b] + Eb_(r)[b];
                         T pm = T(0), ps = T(0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { const T p = av[j] * (bv[j] * Num<T>::prod_scale()); pm = tmax(pm, p); ps += p; }
@@ -436,9 +500,9 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
                     for (int b = lane; b < nblk; b += 32) {
                         T av[8], bv[8];
-                        lds8(sA + b * 8, av);
-                        lds8(sB + b * 8, bv);
-                        const int c = sEa[b] + sEb[b];
+                        lds8(A_(r) + b * 8, av);
+                        lds8(B_(r) + b * 8, bv);
+                        const int c = Ea_(r)[b] + Eb_(r)[b];
                         T pm = T(0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * (bv[j] * Num<T>::prod_scale())) * invZ; pm = tmax(pm, bv[j]); }
@@ -447,9 +511,9 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                         if (wgt == T(0)) continue;
                         T pv[8], left = T(0);
                         if (t >= 1) {
-                            lds8(sAp + b * 8, pv);
+                            lds8(A_(r - 1) + b * 8, pv);
                             if (b > 0)
-                                left = sAp[b * 8 - 1] * Num<T>::exp2i(min(sEp[b - 1] - sEp[b], Num<T>::kMaxShift - 8));
+                                left = A_(r - 1)[b * 8 - 1] * Num<T>::exp2i(min(Ea_(r - 1)[b - 1] - Ea_(r - 1)[b], Num<T>::kMaxShift - 8));
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -467,6 +531,31 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
                     }
                 }
                 __syncwarp();
+            }
+            // ---------------- FCC: posterior, outer product; grad_x row -----------------------------
+            T g0 = T(0), g1 = T(0);
+            if (FCC) {
+                T al0 = T(0), al1 = T(0), be0 = T(0), be1 = T(0);
+                if (lane < lpi) { al0 = Fa_(r)[lane]; be0 = Fb_(r)[lane]; }
+                if (LP > 32 && lane + 32 < lpi) { al1 = Fa_(r)[lane + 32]; be1 = Fb_(r)[lane + 32]; }
+                g0 = al0 * be0; g1 = al1 * be1;
+                const T Z = warp_sum(g0 + g1);
+                const T inv = (Z > T(0)) ? gf / Z : T(0);
+                g0 *= inv; g1 *= inv;
+                if (t >= 1) {                                  // no incoming edge at frame 0
+                    const T winv = inv * Sc_(r);
+                    T wv[RI], pv[CJ];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) wv[i] = Fw_(r)[ib * RI + i] * winv;
+#pragma unroll
+                    for (int j = 0; j < CJ; ++j) pv[j] = Fa_(r - 1)[jb * CJ + j];
+#pragma unroll
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int j = 0; j < CJ; ++j) G[i][j] = fma(wv[i], pv[j], G[i][j]);
+                }
+            }
+            if (FAC) {
                 const T gs = ga * FX::kInvPost;
                 if (lane < L) { g0 = fma(gs, FX::from_fix(bins[lane]), g0); bins[lane] = 0; }
                 if (LP > 32 && lane + 32 < L) { g1 = fma(gs, FX::from_fix(bins[lane + 32]), g1); bins[lane + 32] = 0; }
@@ -475,21 +564,30 @@ __global__ void __launch_bounds__(grad_threads<LP, FCC>(), 1) grad_kernel(const 
             if (lane < L) gx_row[lane] = g0;
             if (LP > 32 && lane + 32 < L) gx_row[lane + 32] = g1;
         }
-        // release the stage (read-only for the consumers apart from winv)
+        // release the stage (read-only for the consumers)
         __syncwarp();
-        if (lane == 0) {
-            if (!arrived_mid) mbar_arrive(&mid[stage]);
-            mbar_arrive(&empty[stage]);
-        }
+        if (lane == 0) mbar_arrive(&empty[stage]);
     }
     flush_fac();
-    if (NO > 0) named_bar_sync(2, (NF + NO) * 32);     // the outer-product warps have parked G in Gf
-    else cbar();
+    cbar();
 
-    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC) ------------------------------------------------------
-    const T *Gf = (const T *)(smem_raw + mp.o_Gf);
+    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC): warps add their G slices in order ----
+    if (FCC) {
+        for (int w = 0; w < NW; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int i = 0; i < RI; ++i)
+#pragma unroll
+                    for (int j = 0; j < CJ; ++j) {
+                        const int gi = ib * RI + i, gj = jb * CJ + j;
+                        if (gi < L && gj < L) Gf[gi * L + gj] += G[i][j];
+                    }
+            }
+            cbar();
+        }
+    }
     T *part = a.partials + (size_t)blockIdx.x * L * L;
-    for (int e = tid; e < L * L; e += nframe) {
+    for (int e = tid; e < L * L; e += ncons) {
         T v = Gal[e];
         if (FCC) v += a.ctx.ehat[e] * Gf[e];
         part[e] = v;
@@ -539,28 +637,24 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     const int L = a.d.L, sp = (int)a.ctx.sp;
     int device = 0;
     cudaGetDevice(&device);
-    // (frames per tile, ring depth): one persistent CTA per SM, one frame per frame warp, as much in flight as fits
-    constexpr int NF = grad_frame_warps<LP>();
-    const int tbs[] = {NF, 8, 4, 2, 1};
-    const int nss[] = {6, 5, 4, 3, 2, 1};
-    int tb = 0, ns = 0;
+    // (frames per tile, ring depth, consumer warps): one persistent CTA per SM, as much in flight as fits
+    static const int cand[][3] = {{16, 5, 8}, {16, 4, 8}, {16, 3, 8}, {8, 4, 8}, {8, 3, 8}, {8, 2, 8}, {4, 3, 4}, {4, 2, 4},
+                                  {2, 2, 2}, {1, 2, 2}, {1, 2, 1}, {1, 1, 1}};
+    int tb = 0, ns = 0, nw = 0;
     size_t bytes = 0;
     int force_tb = 0, force_ns = 0;
     if (const char *env = getenv("ASG_GRAD_TB")) force_tb = atoi(env);
     if (const char *env = getenv("ASG_GRAD_NS")) force_ns = atoi(env);
-    for (int ti = 0; ti < 5 && !tb; ++ti) {
-        if (tbs[ti] > NF || (force_tb && tbs[ti] != force_tb)) continue;
-        for (int ni = 0; ni < 6 && !tb; ++ni) {
-            if (force_ns && nss[ni] != force_ns) continue;
-            if (ti == 0 && nss[ni] < 2 && tbs[1] < NF) continue;     // prefer a shorter tile over an unpipelined ring
-            const size_t b = grad_map(sizeof(T), (size_t)a.ctx.R, L, sp, tbs[ti], nss[ni], NF, FCC, FAC).total;
-            if (b <= 227 * 1024) { tb = tbs[ti]; ns = nss[ni]; bytes = b; }
-        }
+    for (auto &c : cand) {
+        if (force_tb && c[0] != force_tb) continue;
+        if (force_ns && c[1] != force_ns) continue;
+        const size_t b = grad_map(sizeof(T), (size_t)a.ctx.R, L, sp, c[0], c[1], c[2], FCC, FAC).total;
+        if (b <= 227 * 1024) { tb = c[0]; ns = c[1]; nw = c[2]; bytes = b; break; }
     }
     if (!tb) return cudaErrorInvalidValue;
     a.tb = tb;
     a.nstage = ns;
-    a.nwarps = NF;
+    a.nwarps = nw;
     a.dry = getenv("ASG_GRAD_DRY") ? 1 : 0;
     a.tiles_t = (a.d.T + tb - 1) / tb;
     a.num_tiles = a.tiles_t * a.d.N;
@@ -570,7 +664,7 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     if (grid > a.num_tiles) grid = a.num_tiles;
     {
         LaunchScope ls(K_GRAD, st);
-        grad_kernel<T, LP, FCC, FAC><<<grid, grad_threads<LP, FCC>(), bytes, st>>>(a);
+        grad_kernel<T, LP, FCC, FAC><<<grid, (nw + 1) * 32, bytes, st>>>(a);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const int LL = L * L;
