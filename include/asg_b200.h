@@ -68,7 +68,7 @@ enum {
     ASG_E_DTYPE = -1,   /* dtype is not ASG_F32 / ASG_F64 */
     ASG_E_SHAPE = -2,   /* non-positive T/N/L/S, or S > T (asg.py:119-122 truncates before the boundary) */
     ASG_E_NULL = -3,    /* a required pointer is NULL */
-    ASG_E_UNSUPPORTED = -4, /* shape outside what this build covers (see asg_layout) */
+    ASG_E_UNSUPPORTED = -4, /* shape outside what this build covers: L > 2048, S > 4096 (S > 256 when L > 64), fp64 S > 2048 */
     ASG_E_NOGPU = -5    /* no CUDA device / driver: there is no CPU fallback */
 };
 
@@ -101,6 +101,9 @@ typedef struct asg_layout {
     size_t off_fac_hd;        /* [2,N,sp]    exp(H - Rb), exp(D - Rb)                */
     size_t off_lengths;       /* [2,N] int64 copies of il, tl                        */
     size_t off_scalars;       /* [N,8] float64: per-utterance log-scale bookkeeping (scores in f64 etc.) */
+    size_t off_ehat_t;        /* [L,L]       transpose of ehat           (L > 64 only, else = off_ehat)   */
+    size_t off_fmax;          /* [N,tp]      per-frame emission maxima   (L > 64 only)                   */
+    size_t off_rmax;          /* [1]         max A                       (L > 64 only)                   */
 } asg_layout_t;
 
 /* Fills *out.  Returns ASG_E_UNSUPPORTED for shapes this build does not cover. */

@@ -378,3 +378,47 @@ def test_sharded_equals_whole(surf):
     assert np.abs(np.concatenate([p[0] for p in parts]) - loss).max() < 1e-10
     assert np.abs(np.concatenate([p[1] for p in parts], 1) - gx).max() < 1e-12
     assert np.abs(parts[0][2] + parts[1][2] - gA).max() < 1e-10
+
+
+# ----------------------------------------------------------------------------------------------
+# large alphabets (L > 64): E no longer fits on chip -- separate kernels, same records, same ABI
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float64, TOL64)])
+@pytest.mark.parametrize("path", ["fast", "serial", "fwdonly"])
+def test_large_alphabet_small_case(surf, dtype, tol, path):
+    """L = 100 (> 64), ragged lengths, N not a multiple of the scan's utterance group, -inf transitions."""
+    r = np.random.default_rng(21)
+    T, N, L, S = 37, 6, 100, 11
+    x = r.standard_normal((T, N, L))
+    A = 0.5 * r.standard_normal((L, L))
+    A[3, 7] = -np.inf
+    y = r.integers(0, L, (N, S))
+    tl = r.integers(1, S + 1, N)
+    il = np.array([r.integers(max(tl[n], T // 2), T + 1) for n in range(N)])
+    g = r.uniform(0.5, 1.5, N)
+    ref = O.asg_loss(x, y, A, il, tl, g)
+    c = {"x": x, "y": y, "A": A, "il": il, "tl": tl, "g": g}
+    o = run_surface(surf, c, dtype, path)
+    for k, v in o.items():
+        floor = 1.0 if k in ("loss", "full", "aligned") else 1e-30
+        assert rel(v, ref[k], floor) <= tol, (path, k, rel(v, ref[k], floor))
+
+
+def test_cfg4_large_alphabet(surf):
+    """T=500 N=128 L=1024 S=100 fp32 (BASELINE configs[3]): the reference cannot run this with a backward pass
+    (268 GB path_contrib).  Properties on the whole batch + oracle parity on 2 utterances."""
+    T, N, L, S = 500, 128, 1024, 100
+    x, A, y, il, tl, gg = _synthetic(T, N, L, S, seed=6, varlen=True)
+    loss, gx, gA = _run_cfg(surf, x, A, y, il, tl, gg, torch.float32)
+    assert np.isfinite(loss).all() and (loss > 0).all()
+    assert np.abs(gx.sum(-1)).max() < 5e-5
+    for n in range(0, N, 17):
+        assert (gx[int(il[n]):, n] == 0).all()
+    assert abs(gA.sum()) < 1e-3 * np.abs(gA).max() * L
+    sel = [0, 127]
+    ref = O.asg_loss(x[:, sel].numpy(), y[sel].numpy(), A.numpy(), il[sel].numpy(), tl[sel].numpy(), gg[sel].numpy())
+    assert rel(loss[sel], ref["loss"], 1.0) <= TOL32
+    assert rel(gx[:, sel], ref["gx"]) <= TOL32
+    l3, gx3, gA3 = _run_cfg(surf, x[:, sel], A, y[sel], il[sel], tl[sel], gg[sel], torch.float32)
+    assert rel(gA3, ref["gA"]) <= TOL32
+    assert rel(gx3, ref["gx"]) <= TOL32

@@ -23,7 +23,7 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-ccbin", CXX]
-CU_SOURCES = ["asg_scan.cu", "asg_grad.cu", "asg_api.cu"]
+CU_SOURCES = ["asg_scan.cu", "asg_grad.cu", "asg_large.cu", "asg_api.cu"]
 HEADERS = [os.path.join(CSRC, "asg_common.cuh"), os.path.join(CSRC, "asg_internal.h"),
            os.path.join(INC, "asg_b200.h")]
 
@@ -53,7 +53,7 @@ def build_lib(verbose=False):
             raise RuntimeError("nvcc failed on " + src)
     if procs or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + [
-               "-cudart", "shared", "-ccbin", CXX,
+               "-cudart", "shared", "-lcublas", "-ccbin", CXX,
                "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
         if verbose:
             print(" ".join(cmd), flush=True)

@@ -81,7 +81,9 @@ static int check_dims(int dtype, int64_t T, int64_t N, int64_t L, int64_t S) {
         return fail(ASG_E_SHAPE, "T, N, L, S must be positive (got %lld, %lld, %lld, %lld)", (long long)T, (long long)N,
                     (long long)L, (long long)S);
     if (S > T) return fail(ASG_E_SHAPE, "S (%lld) > T (%lld): truncate targets first (asg.py:119-122)", (long long)S, (long long)T);
-    if (L > 64) return fail(ASG_E_UNSUPPORTED, "this build covers L <= 64 labels (got %lld)", (long long)L);
+    if (L > 2048) return fail(ASG_E_UNSUPPORTED, "this build covers L <= 2048 labels (got %lld)", (long long)L);
+    if (L > ASG_SMALL_L && S > 256)
+        return fail(ASG_E_UNSUPPORTED, "large alphabets (L > 64) are covered for S <= 256 target positions (got %lld)", (long long)S);
     if (S > 4096) return fail(ASG_E_UNSUPPORTED, "this build covers S <= 4096 target positions (got %lld)", (long long)S);
     if (T > (1 << 24) || N > (1 << 20)) return fail(ASG_E_UNSUPPORTED, "T or N too large");
     return 0;
@@ -104,6 +106,7 @@ static int scan_typed(int roles, const void *x, int64_t x_st, int64_t x_sn, int6
     a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
     a.ctx = make_ctx<T>(state, ctx, lay, N);
     a.full_scores = (T *)full_scores; a.aligned_scores = (T *)aligned_scores;
+    a.fmax = nullptr;
     a.dir0 = a.dir1 = 0; a.fcc_dirs = a.fac_dirs = 0;
     return launch_scan<T>(a, roles, stream);
 }
@@ -121,6 +124,7 @@ static int grad_typed(int parts, const void *g_full, int64_t gfs, const void *g_
     a.grad_x = (T *)grad_x; a.grad_A = (T *)grad_A;
     a.partials = (T *)scratch;
     a.tb = 0; a.nstage = 0; a.nwarps = 0; a.dry = 0; a.tiles_t = 0; a.num_tiles = 0;
+    if (L > ASG_SMALL_L) return launch_grad_large<T>(a, parts, stream);
     return launch_grad<T>(a, parts, stream);
 }
 
@@ -178,10 +182,18 @@ int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout
     out->off_fac_hd = take(eb * 2 * (size_t)N * out->sp);
     out->off_lengths = take(sizeof(int64_t) * 2 * (size_t)N);
     out->off_scalars = take(sizeof(double) * 8 * (size_t)N);
+    out->off_ehat_t = out->off_ehat;
+    if (L > ASG_SMALL_L) {
+        out->off_ehat_t = take(eb * (size_t)L * L);
+        out->off_fmax = take(eb * (size_t)N * out->tp);
+        out->off_rmax = take(eb);
+    }
     out->ctx_bytes = off;
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) device = -1;
     out->grad_scratch_bytes = align_up(eb * (size_t)grad_grid_size(device) * L * L, 256);
+    if (L > ASG_SMALL_L)   // G [L,L] + the FAC edge sums [2,N,sp] in 64-bit fixed point
+        out->grad_scratch_bytes = align_up(eb * (size_t)L * L, 256) + align_up(16 * (size_t)N * out->sp, 256);
     return 0;
 }
 

@@ -12,6 +12,9 @@ template <typename T> struct Ctx {
     int64_t R;        // record size in bytes
     int o_fa, o_fb, o_ea, o_eb, o_ca, o_cb, o_cw, o_sc;   // byte offsets of the parts inside a record
     T *ehat;          // [L,L]
+    T *ehat_t;        // [L,L]  transpose (large alphabets only)
+    T *fmax;          // [N,tp] per-frame emission maxima (large alphabets only)
+    T *rmax;          // [1]    max A (large alphabets only)
     T *fac_hd;        // [2,N,sp]   h_s, d_s (edge s -> s+1)
     int64_t *il;      // [N]
     int64_t *tl;      // [N]
@@ -40,6 +43,9 @@ template <typename T> inline Ctx<T> make_ctx(void *state, void *blob, const asg_
     c.o_fa = (int)lay.rec_fac_alpha; c.o_fb = (int)lay.rec_fac_beta; c.o_ea = (int)lay.rec_fac_ea; c.o_eb = (int)lay.rec_fac_eb;
     c.o_ca = (int)lay.rec_fcc_alpha; c.o_cb = (int)lay.rec_fcc_beta; c.o_cw = (int)lay.rec_fcc_w; c.o_sc = (int)lay.rec_fcc_scale;
     c.ehat = reinterpret_cast<T *>(b + lay.off_ehat);
+    c.ehat_t = reinterpret_cast<T *>(b + lay.off_ehat_t);
+    c.fmax = reinterpret_cast<T *>(b + lay.off_fmax);
+    c.rmax = reinterpret_cast<T *>(b + lay.off_rmax);
     c.fac_hd = reinterpret_cast<T *>(b + lay.off_fac_hd);
     c.il = reinterpret_cast<int64_t *>(b + lay.off_lengths);
     c.tl = c.il + N;
@@ -64,6 +70,7 @@ template <typename T> struct ScanArgs {
     Dims d;
     Ctx<T> ctx;                 // ctx.rec == nullptr: forward-only, nothing is stored
     T *full_scores, *aligned_scores;
+    const T *fmax;              // large alphabets: per-frame emission maxima [N,tp] from the prepass (NULL otherwise)
     int dir0, dir1;             // direction (0 = alpha, 1 = beta) served by blockIdx.y = 0 / 1
     int fcc_dirs, fac_dirs;     // bit d set: that lattice runs direction d
 };
@@ -87,6 +94,11 @@ template <typename T> struct GradArgs {
 // launchers (asg_scan.cu / asg_grad.cu); return cudaError_t as int
 template <typename T> int launch_scan(const ScanArgs<T> &a, int roles, cudaStream_t stream);
 template <typename T> int launch_grad(const GradArgs<T> &a, int parts, cudaStream_t stream);
+// large-alphabet path (asg_large.cu), L > ASG_SMALL_L
+constexpr int ASG_SMALL_L = 64;
+template <typename T> int large_prepare(const ScanArgs<T> &a, cudaStream_t stream);
+template <typename T> int launch_fcc_large(const ScanArgs<T> &a, int ndirs, cudaStream_t stream);
+template <typename T> int launch_grad_large(const GradArgs<T> &a, int parts, cudaStream_t stream);
 int grad_grid_size(int device);   // number of persistent CTAs asg_grad launches
 void count_launch(int n = 1);
 

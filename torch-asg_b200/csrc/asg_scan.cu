@@ -39,8 +39,11 @@ constexpr int RING = NRAW * FB;   // depth of the u ring, in frames
 template <typename T, bool BETA, typename ConsumedFn, typename FlushFn>
 __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int rp, T *uring, int up, int *produced,
                                               double *msum_out, int *msum_ready, ConsumedFn consumed_min, FlushFn flush,
-                                              int ngroups, int n, int Tn, int lane) {
-    const int L = a.d.L;
+                                              int ngroups, int n, int Tn, int lane, const int *glab = nullptr, int glen = 0) {
+    // glab != NULL (large alphabets): gather mode -- a ring row holds u_t[y_s] for the target positions s < glen
+    // (labels glab[s], -1 = padding) instead of all L labels; the frame maximum comes from the prepass (a.fmax)
+    const bool gather = glab != nullptr;
+    const int L = gather ? glen : a.d.L;
     const int f = lane >> 2, sub = lane & 3;
     const T *xn = a.x + (int64_t)n * a.x_sn;
     const T ninf = Num<T>::neg_inf();
@@ -50,7 +53,12 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
             const int t = BETA ? (Tn - 1 - k) : k;
             const T *row = xn + (int64_t)t * a.x_st;
             T *dst = raw + ((size_t)(b % NRAW) * FB + f) * rp;
-            for (int l = sub; l < L; l += 4) cp_async<sizeof(T)>(dst + l, row + (int64_t)l * a.x_sl);
+            if (gather) {
+                for (int l = sub; l < L; l += 4) { const int lb = glab[l]; if (lb >= 0) cp_async<sizeof(T)>(dst + l, row + (int64_t)lb * a.x_sl); }
+                if (sub == 0) cp_async<sizeof(T)>(dst + rp - 1, a.fmax + (int64_t)n * a.ctx.tp + t);
+            } else {
+                for (int l = sub; l < L; l += 4) cp_async<sizeof(T)>(dst + l, row + (int64_t)l * a.x_sl);
+            }
         }
     };
     const int nb = (Tn + FB - 1) / FB;
@@ -75,14 +83,15 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
             const bool valid = k < Tn;
             const T *src = raw + ((size_t)(b % NRAW) * FB + f) * rp;
             T m = ninf;
-            if (valid)
+            if (valid && !gather)
                 for (int l = sub; l < L; l += 4) m = tmax(m, src[l]);
+            if (valid && gather) m = src[rp - 1];
             m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 1));
             m = tmax(m, __shfl_xor_sync(ASG_FULL_MASK, m, 2));
             if (!(m > ninf)) m = T(0);                     // an all -inf frame
             T *dst = uring + (size_t)(k % RING) * up;
             if (valid)                                     // (slots of frames >= Tn belong to frames not yet consumed)
-                for (int l = sub; l < up; l += 4) dst[l] = (l < L) ? Num<T>::exp_(src[l] - m) : T(0);
+                for (int l = sub; l < up; l += 4) dst[l] = (l < L && (!gather || glab[l] >= 0)) ? Num<T>::exp_(src[l] - m) : T(0);
             if (valid && sub == 0) msum += (double)m;
             if (b + NRAW < nb) issue(b + NRAW);            // each lane re-fills only elements it has consumed itself
             cp_async_commit();
@@ -570,7 +579,7 @@ __host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
     const int up = lpi + 4;
-    size_t o_raw = take(sizeof(T) * NRAW * FB * lpi);
+    size_t o_raw = take(sizeof(T) * NRAW * FB * up);
     size_t o_uring = take(sizeof(T) * RING * up);
     size_t o_xval = take(sizeof(T) * 2 * (W + 1));
     size_t o_xexp = take(sizeof(int) * 2 * (W + 1));
@@ -598,7 +607,7 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
                              const T (&h)[ASG_BLK], const T (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
     // dd[j]: alpha -> edge (s-1 -> s) into own state j;  beta -> edge (s -> s+1) out of own state j
     const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp;
-    const int up = (int)a.ctx.lpi + 4;
+    const int up = (a.fmax ? (int)a.ctx.sp : (int)a.ctx.lpi) + 4;
     const int64_t tp = a.ctx.tp;
     const int gl = warp * 32 + lane;            // global lane = block index
     const int s0 = gl * ASG_BLK;
@@ -757,7 +766,7 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
                                  const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int lane) {
     typedef float T;
     const int sp = (int)a.ctx.sp, nblk = (int)a.ctx.nblk, nbp = (int)a.ctx.nbp;
-    const int up = (int)a.ctx.lpi + 4;
+    const int up = (a.fmax ? (int)a.ctx.sp : (int)a.ctx.lpi) + 4;
     const int64_t tp = a.ctx.tp;
     const int s0 = lane * ASG_BLK;
     const bool owns = s0 < sp;
@@ -932,7 +941,9 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
     extern __shared__ __align__(16) char smem_raw[];
     FacSmemView<T> sm;
     const int L = a.d.L, S = a.d.S;
-    const int sp = (int)a.ctx.sp, lpi = (int)a.ctx.lpi, up = lpi + 4;
+    const int sp = (int)a.ctx.sp;
+    const int lpi = a.fmax ? sp : (int)a.ctx.lpi;     // entries per ring row: all labels, or (large alphabets) the target positions
+    const int up = lpi + 4;
     fac_smem_carve<T>(&sm, smem_raw, lpi, sp, W);
     const int n = blockIdx.x;
     const int dir = blockIdx.y == 0 ? a.dir0 : a.dir1;
@@ -966,10 +977,10 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
 #pragma unroll
         for (int j = 0; j < ASG_BLK; ++j) {
             const int s = s0 + j;
-            Hs[j] = ninf; Ds[j] = ninf; lab[j] = lpi;
+            Hs[j] = ninf; Ds[j] = ninf; lab[j] = lpi;         // lpi = the always-zero slot of a ring row
             if (s < Sn) {
                 const int c = sm.ylab[s];
-                lab[j] = c;
+                lab[j] = a.fmax ? s : c;                       // gather mode: the ring row is indexed by position
                 Hs[j] = a.A[c * a.A_s0 + c * a.A_s1];
                 if (s + 1 < Sn) { const int nx = sm.ylab[s + 1]; Ds[j] = a.A[nx * a.A_s0 + c * a.A_s1]; }
                 if (Hs[j] < -ninf) lmax = tmax(lmax, Hs[j]);
@@ -990,8 +1001,8 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
             for (int q = 0; q < W; ++q) c = min(c, ld_volatile_s32(&sm.consumed[q]));
             return c;
         };
-        if (dir == 0) scan_producer<T, false>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, [](int) {}, 0, n, Tn, lane);
-        else scan_producer<T, true>(a, sm.raw, lpi, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, [](int) {}, 0, n, Tn, lane);
+        if (dir == 0) scan_producer<T, false>(a, sm.raw, up, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, [](int) {}, 0, n, Tn, lane, a.fmax ? sm.ylab : nullptr, sp);
+        else scan_producer<T, true>(a, sm.raw, up, sm.uring, up, &sm.flags[0], sm.msum, &sm.flags[1], cons, [](int) {}, 0, n, Tn, lane, a.fmax ? sm.ylab : nullptr, sp);
         return;
     }
     T h[ASG_BLK], dout[ASG_BLK];
@@ -1077,7 +1088,7 @@ template <typename T> static cudaError_t launch_fac(const ScanArgs<T> &a, int nd
     int W = 1;
     while (W * 32 < lanes) W <<= 1;
     if (W > 16) return cudaErrorInvalidValue;
-    const size_t bytes = fac_smem_carve<T>(nullptr, nullptr, (int)a.ctx.lpi, (int)a.ctx.sp, W);
+    const size_t bytes = fac_smem_carve<T>(nullptr, nullptr, a.fmax ? (int)a.ctx.sp : (int)a.ctx.lpi, (int)a.ctx.sp, W);
     if (bytes > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(fac_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -1096,6 +1107,10 @@ template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaSt
     const bool fcc_a = roles & ASG_ROLE_FCC_ALPHA, fcc_b = roles & ASG_ROLE_FCC_BETA;
     const bool fac_a = roles & ASG_ROLE_FAC_ALPHA, fac_b = roles & ASG_ROLE_FAC_BETA;
     const bool any_fcc = fcc_a || fcc_b, any_fac = fac_a || fac_b;
+    if (a_in.d.L > ASG_SMALL_L) {      // E, E^T, max A and the per-frame emission maxima, before the streams fork
+        int rc = large_prepare<T>(a_in, stream);
+        if (rc) return rc;
+    }
     cudaStream_t side = nullptr;
     if (any_fcc && any_fac) {
         // the FAC scans run beside the FCC scans: fork a side stream off the caller's stream, join after
@@ -1104,16 +1119,20 @@ template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaSt
         if ((e = cudaEventRecord(fork, stream)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return (int)e;
     }
+    const bool large = a_in.d.L > ASG_SMALL_L;
     if (any_fcc) {
         ScanArgs<T> a = a_in;
         a.dir0 = fcc_a ? 0 : 1;
         a.dir1 = 1;
-        if ((e = launch_fcc<T>(a, (fcc_a && fcc_b) ? 2 : 1, stream)) != cudaSuccess) return (int)e;
+        const int nd = (fcc_a && fcc_b) ? 2 : 1;
+        if (large) { int rc = launch_fcc_large<T>(a, nd, stream); if (rc) return rc; }
+        else if ((e = launch_fcc<T>(a, nd, stream)) != cudaSuccess) return (int)e;
     }
     if (any_fac) {
         ScanArgs<T> a = a_in;
         a.dir0 = fac_a ? 0 : 1;
         a.dir1 = 1;
+        if (large) a.fmax = a.ctx.fmax;        // gather mode
         cudaStream_t st = side ? side : stream;
         if ((e = launch_fac<T>(a, (fac_a && fac_b) ? 2 : 1, st)) != cudaSuccess) return (int)e;
         if (side) {
