@@ -28,7 +28,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-PKG = os.path.join(ROOT, "torch-asg_b200")
+PKG = os.environ.get("ASG_PKG") or os.path.join(ROOT, "torch-asg_b200")      # ASG_PKG: A/B builds (developer)
 for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -327,9 +327,11 @@ def run_b200(args):
 
     # ---- end to end through the C ABI with host buffers (rank-local, all ranks concurrently) ----------
     # NCTX host contexts in flight (asg_host_submit / asg_host_wait): every step still copies its inputs from
-    # pinned host memory and its results (loss, grad_x, grad_A) back, but step i's H2D overlaps step i-1's
-    # kernels and step i-2's D2H.
-    NCTX = 3
+    # pinned host memory and its results (loss, grad_x, grad_A) back, but step i's H2D overlaps the kernels of the
+    # steps before it and the D2H of older ones.  Each context owns a stream (and its scans' side stream); the
+    # scans of several steps share the GPU (they fill ~2 small CTAs per SM), so throughput ends up bound by the
+    # PCIe copies (10 MB each way per step) rather than by one step's scan latency.
+    NCTX = int(os.environ.get("ASG_BENCH_NCTX", "8"))
     hx = xs[0].detach().cpu().pin_memory()
     hA = A.clone().pin_memory()
     hy = ys[0].cpu().pin_memory()

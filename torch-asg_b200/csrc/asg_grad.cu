@@ -31,7 +31,7 @@
 
 namespace asg {
 
-constexpr int GRAD_MAX_CWARPS = 8;     // consumer warps (+ one producer warp)
+constexpr int GRAD_MAX_CWARPS = 12;    // consumer warps (+ the producer's warpgroup)
 constexpr int GRAD_LBINS = 72;         // label bins per warp: L <= 64, bin L = trash (padding positions)
 
 // Fixed-point images (integers add in any order with the same result, so shared-memory atomics stay deterministic):
@@ -80,13 +80,13 @@ __host__ __device__ inline GradMap grad_map(size_t eb, size_t rec_bytes, int L, 
     m.oWinv = take(fcc ? eb * (size_t)((TB + 3) / 4 * 4) : 0);
     m.stage_bytes = align_up(off, 128);
     off = 0;
-    m.o_hh = take(fac ? eb * sp : 0);
-    m.o_din = take(fac ? eb * sp : 0);
+    m.o_hh = take(fac ? 2 * eb * sp : 0);        // [2][sp]: alternate by utterance (narrow mode)
+    m.o_din = take(fac ? 2 * eb * sp : 0);
     m.o_ylab = take(fac ? sizeof(int) * sp : 0);
     m.o_Gal = take(eb * (size_t)L * L);
     m.o_Gf = take(fcc ? eb * (size_t)L * L : 0);
     m.o_galfix = take(fac ? 8 * 2 * (size_t)L * L : 0);
-    m.o_bins = take(fac ? 8 * (size_t)nw * 2 * GRAD_LBINS : 0);
+    m.o_bins = take(fac ? eb * (size_t)nw * 2 * GRAD_LBINS : 0);      // int32 bins for float, int64 for double
     m.o_acc = take((fac && sp > 256) ? eb * (size_t)nw * 2 * sp : 0);
     m.o_bars = take(sizeof(uint64_t) * 3 * 8);
     m.o_stages = align_up(off, 128);
@@ -109,7 +109,7 @@ __device__ __forceinline__ void lds8(const double *p, double (&v)[8]) {
 }
 
 template <typename T, int LP, bool FCC, bool FAC>
-__global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(const GradArgs<T> a) {
+__global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(const GradArgs<T> a) {
     extern __shared__ __align__(128) char smem_raw[];
     typedef typename Fix<T>::bin_t bin_t;
     const int L = a.d.L, N = a.d.N, Tt = a.d.T;
@@ -137,10 +137,16 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(con
     }
     __syncthreads();
 
+    // Register budget: the consumer warps fill whole warpgroups (idle warps of a partly used group just leave), the
+    // producer sits in a warpgroup of its own and hands its registers back (setmaxnreg), so the frame warps keep all
+    // their accumulators in registers: 16 warps launch with 128 registers each, the producer group keeps 32, the
+    // twelve frame warps get 160.
+    const int PW = (NW + 3) & ~3;                  // first warp of the producer's warpgroup
     // =========================== producer warp: ONE bulk copy per tile ================================
     // records t0-1 .. t0+rows-1 of the utterance are one contiguous chunk of the state array
-    if (warp == NW) {
-        if (lane == 0) {
+    if (warp >= PW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+        if (warp == PW && lane == 0) {
             int n = q_begin / a.tiles_t, tt = q_begin - n * a.tiles_t;     // walked, no per-tile divisions
             int Tn = (q_begin < q_end) ? (int)a.ctx.il[n] : 0;
             int stage = 0, use = 0;
@@ -165,6 +171,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(con
         }
         return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;\n");
+    if (warp >= NW) return;
 
     // =========================== consumer warps =====================================================
     auto cbar = [&]() { named_bar_sync(1, ncons); };
@@ -571,8 +579,27 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 1) * 32, 1) grad_kernel(con
     flush_fac();
     cbar();
 
-    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC): warps add their G slices in order ----
-    if (FCC) {
+    // ---- per-CTA partial of grad_A = E o G (FCC) + Gal (FAC) ----
+    // Every tile has been consumed, so the tile ring is idle: each warp parks its G slice there and, after ONE
+    // barrier, the element owners add the NW slices in warp order (fixed order: deterministic).  When the ring is
+    // too small for NW slices (tiny tiles) the warps take turns instead.
+    const bool park = !a.nopark && (size_t)NW * L * L * sizeof(T) <= (size_t)NS * mp.stage_bytes;
+    if (FCC && park) {
+        T *slice = (T *)stages + (size_t)warp * L * L;
+#pragma unroll
+        for (int i = 0; i < RI; ++i)
+#pragma unroll
+            for (int j = 0; j < CJ; ++j) {
+                const int gi = ib * RI + i, gj = jb * CJ + j;
+                if (gi < L && gj < L) slice[gi * L + gj] = G[i][j];
+            }
+        cbar();
+        for (int e = tid; e < L * L; e += ncons) {
+            T v = T(0);
+            for (int w = 0; w < NW; ++w) v += ((const T *)stages)[(size_t)w * L * L + e];
+            Gf[e] = v;
+        }
+    } else if (FCC) {
         for (int w = 0; w < NW; ++w) {
             if (warp == w) {
 #pragma unroll
@@ -638,7 +665,7 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     int device = 0;
     cudaGetDevice(&device);
     // (frames per tile, ring depth, consumer warps): one persistent CTA per SM, as much in flight as fits
-    static const int cand[][3] = {{16, 5, 8}, {16, 4, 8}, {16, 3, 8}, {8, 4, 8}, {8, 3, 8}, {8, 2, 8}, {4, 3, 4}, {4, 2, 4},
+    static const int cand[][3] = {{24, 3, 12}, {16, 5, 8}, {16, 4, 8}, {16, 3, 8}, {8, 4, 8}, {8, 3, 8}, {8, 2, 8}, {4, 3, 4}, {4, 2, 4},
                                   {2, 2, 2}, {1, 2, 2}, {1, 2, 1}, {1, 1, 1}};
     int tb = 0, ns = 0, nw = 0;
     size_t bytes = 0;
@@ -656,6 +683,7 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     a.nstage = ns;
     a.nwarps = nw;
     a.dry = getenv("ASG_GRAD_DRY") ? 1 : 0;
+    a.nopark = getenv("ASG_GRAD_NOPARK") ? 1 : 0;
     a.tiles_t = (a.d.T + tb - 1) / tb;
     a.num_tiles = a.tiles_t * a.d.N;
     cudaError_t e = cudaFuncSetAttribute(grad_kernel<T, LP, FCC, FAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -664,7 +692,7 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     if (grid > a.num_tiles) grid = a.num_tiles;
     {
         LaunchScope ls(K_GRAD, st);
-        grad_kernel<T, LP, FCC, FAC><<<grid, (nw + 1) * 32, bytes, st>>>(a);
+        grad_kernel<T, LP, FCC, FAC><<<grid, (((nw + 3) & ~3) + 4) * 32, bytes, st>>>(a);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const int LL = L * L;

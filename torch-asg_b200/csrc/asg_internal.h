@@ -87,6 +87,7 @@ template <typename T> struct GradArgs {
     int nstage;                 // depth of the shared-memory tile ring
     int nwarps;                 // consumer warps per CTA
     int dry;                    // diagnostics: move the data, skip the arithmetic (ASG_GRAD_DRY)
+    int nopark;                 // diagnostics: serial per-warp reduction of the edge sums (ASG_GRAD_NOPARK)
     int tiles_t;                // ceil(T / tb)
     int num_tiles;              // tiles_t * N
 };

@@ -21,6 +21,9 @@
 //        exponent per lane), neighbours exchanged with one shuffle; no warp-wide reduction at all.
 // State is written utterance-major ([N,tp,*], see asg_layout_t): every chain writes one sequential stream.
 // See DESIGN.md for the numerics and tests/scaled_model.py for the executable specification.
+#include <mutex>
+#include <vector>
+
 #include "asg_common.cuh"
 #include "asg_internal.h"
 
@@ -1044,17 +1047,24 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
 // =============================================================================================
 // launchers
 // =============================================================================================
-static cudaStream_t side_stream(int device) {
-    static cudaStream_t streams[64] = {0};
-    if (device < 0 || device >= 64) return nullptr;
-    if (!streams[device]) cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
-    return streams[device];
-}
-static cudaEvent_t pooled_event(int device, int which) {
-    static cudaEvent_t ev[64][2] = {{0}};
-    if (device < 0 || device >= 64) return nullptr;
-    if (!ev[device][which]) cudaEventCreateWithFlags(&ev[device][which], cudaEventDisableTiming);
-    return ev[device][which];
+// The FAC scans run beside the FCC scans on a side stream.  Every (device, caller stream) pair owns its side
+// stream and its fork/join events, so independent callers (several host contexts in flight, several host
+// threads) neither serialise on one shared side stream nor re-record each other's events.
+struct SideSlot { int device; cudaStream_t key, side; cudaEvent_t fork, join; };
+static bool side_slot(int device, cudaStream_t key, SideSlot &out) {
+    static std::mutex mu;
+    static std::vector<SideSlot> slots;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const SideSlot &s : slots)
+        if (s.device == device && s.key == key) { out = s; return true; }
+    if (slots.size() >= 256) return false;          // beyond that: the caller's stream runs both (still correct)
+    SideSlot s{device, key, nullptr, nullptr, nullptr};
+    if (cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return false;
+    slots.push_back(s);
+    out = s;
+    return true;
 }
 
 template <typename T, int LP>
@@ -1112,12 +1122,12 @@ template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaSt
         if (rc) return rc;
     }
     cudaStream_t side = nullptr;
-    if (any_fcc && any_fac) {
-        // the FAC scans run beside the FCC scans: fork a side stream off the caller's stream, join after
-        side = side_stream(device);
-        cudaEvent_t fork = pooled_event(device, 0);
-        if ((e = cudaEventRecord(fork, stream)) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return (int)e;
+    SideSlot slot{};
+    if (any_fcc && any_fac && side_slot(device, stream, slot)) {
+        // fork the side stream off the caller's stream, join after
+        side = slot.side;
+        if ((e = cudaEventRecord(slot.fork, stream)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(side, slot.fork, 0)) != cudaSuccess) return (int)e;
     }
     const bool large = a_in.d.L > ASG_SMALL_L;
     if (any_fcc) {
@@ -1136,9 +1146,8 @@ template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaSt
         cudaStream_t st = side ? side : stream;
         if ((e = launch_fac<T>(a, (fac_a && fac_b) ? 2 : 1, st)) != cudaSuccess) return (int)e;
         if (side) {
-            cudaEvent_t join = pooled_event(device, 1);
-            if ((e = cudaEventRecord(join, side)) != cudaSuccess) return (int)e;
-            if ((e = cudaStreamWaitEvent(stream, join, 0)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventRecord(slot.join, side)) != cudaSuccess) return (int)e;
+            if ((e = cudaStreamWaitEvent(stream, slot.join, 0)) != cudaSuccess) return (int)e;
         }
     }
     return 0;
