@@ -2,5 +2,5 @@
 reps=$1; shift
 for i in $(seq 1 $reps); do for spec in "$@"; do
 envs=""; p="$spec"; case "$spec" in *:*) envs="${spec%%:*}"; p="${spec#*:}";; esac
-env $envs ASG_PKG=$PWD/$p ASG_BENCH_NCTX=8 python bench.py --steps 200 --warmup 10 --no-cpu-baseline | python -c "import sys,json; d=json.loads(sys.stdin.read()); k=d['kernels']; print('$spec', round(d['value']), round(d['ms_per_step']*1e3,1), 'e2e', round(d['e2e']['value']), {n: round(v['avg_us'],1) for n,v in k.items()})"
+env $envs ASG_PKG=$PWD/$p ASG_BENCH_NCTX=8 python bench.py --steps 200 --warmup 10 --no-cpu-baseline | python tools/ab_fmt.py "$spec"
 done; done

@@ -69,7 +69,7 @@ __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 // frame t0-1 first) exactly as they lie in global memory, plus the tile's winv scalars.
 struct GradMap {
     size_t oRec, oWinv, stage_bytes;                                   // per stage, byte offsets from the stage base
-    size_t o_hh, o_din, o_ylab, o_Gal, o_Gf, o_galfix, o_bins, o_acc, o_bars, o_stages, total;   // per CTA
+    size_t o_hh, o_din, o_ylab, o_cscal, o_Gal, o_Gf, o_galfix, o_bins, o_acc, o_bars, o_stages, total;   // per CTA
 };
 
 __host__ __device__ inline GradMap grad_map(size_t eb, size_t rec_bytes, int L, int sp, int TB, int nstage, int nw, bool fcc, bool fac) {
@@ -80,9 +80,11 @@ __host__ __device__ inline GradMap grad_map(size_t eb, size_t rec_bytes, int L, 
     m.oWinv = take(fcc ? eb * (size_t)((TB + 3) / 4 * 4) : 0);
     m.stage_bytes = align_up(off, 128);
     off = 0;
-    m.o_hh = take(fac ? 2 * eb * sp : 0);        // [2][sp]: alternate by utterance (narrow mode)
-    m.o_din = take(fac ? 2 * eb * sp : 0);
-    m.o_ylab = take(fac ? sizeof(int) * sp : 0);
+    const size_t nb = sp <= 256 ? 2 : 1;         // narrow mode: the utterance constants are double-buffered (prefetch warp)
+    m.o_hh = take(fac ? nb * eb * sp : 0);
+    m.o_din = take(fac ? nb * eb * sp : 0);
+    m.o_ylab = take(fac ? nb * sizeof(int) * sp : 0);
+    m.o_cscal = take(2 * 2 * eb + 2 * 2 * sizeof(int));      // [2]{gf, ga} then [2]{Tn, Sn}
     m.o_Gal = take(eb * (size_t)L * L);
     m.o_Gf = take(fcc ? eb * (size_t)L * L : 0);
     m.o_galfix = take(fac ? 8 * 2 * (size_t)L * L : 0);
@@ -124,7 +126,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     T *hh = (T *)(smem_raw + mp.o_hh), *din = (T *)(smem_raw + mp.o_din);
     T *Gal = (T *)(smem_raw + mp.o_Gal), *Gf = (T *)(smem_raw + mp.o_Gf);
     int *ylab = (int *)(smem_raw + mp.o_ylab);
-    uint64_t *full = (uint64_t *)(smem_raw + mp.o_bars), *empty = full + 8;
+    uint64_t *full = (uint64_t *)(smem_raw + mp.o_bars), *empty = full + 8, *cfull = full + 16, *cempty = full + 18;
+    T *cscalT = (T *)(smem_raw + mp.o_cscal);
+    int *cscalI = (int *)(cscalT + 4);
     char *stages = smem_raw + mp.o_stages;
 
     // balanced contiguous tile ranges
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&cfull[b], 96); mbar_init(&cempty[b], NW); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -144,8 +149,45 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     const int PW = (NW + 3) & ~3;                  // first warp of the producer's warpgroup
     // =========================== producer warp: ONE bulk copy per tile ================================
     // records t0-1 .. t0+rows-1 of the utterance are one contiguous chunk of the state array
+    const bool prefetch = (nblk <= 32) || !FAC;      // narrow targets: a helper warp stages the next utterance's constants
     if (warp >= PW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+        if (warp > PW && prefetch && q_begin < q_end) {
+            // ---- utterance constants one utterance ahead, into the buffer the frame warps released: no global-memory
+            //      latency at an utterance switch.  Three helper warps: labels | h | d (+ the scalars), every lane's loads
+            //      issued together (sp <= 256: at most 8 per lane).
+            const int role = warp - PW;             // 1: labels, 2: h, 3: d and scalars
+            const int n_first = q_begin / a.tiles_t, n_last = (q_end - 1) / a.tiles_t;
+            for (int n = n_first, k = 0; n <= n_last; ++n, ++k) {
+                const int buf = k & 1;
+                mbar_wait(&cempty[buf], ((k >> 1) & 1) ^ 1);
+                const int Sn_ = FAC ? (int)a.ctx.tl[n] : 0;
+                if (FAC && role == 1) {
+                    const int64_t *yn = a.y + (int64_t)n * a.y_s0;
+                    int64_t v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int s = lane + 32 * i; v[i] = (s < Sn_) ? yn[(int64_t)s * a.y_s1] : (int64_t)L; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int s = lane + 32 * i; if (s < sp) ylab[buf * sp + s] = (s < Sn_) ? max(0, min(L - 1, (int)v[i])) : L; }
+                } else if (FAC) {
+                    const T *src = a.ctx.fac_hd + (role == 2 ? (int64_t)n * sp : ((int64_t)N + n) * sp - 1);
+                    T *dst = (role == 2 ? hh : din) + buf * sp;
+                    const int lo = role == 2 ? 0 : 1;
+                    T v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int s = lane + 32 * i; v[i] = (s >= lo && s < Sn_) ? src[s] : T(0); }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int s = lane + 32 * i; if (s < sp) dst[s] = v[i]; }
+                }
+                if (role == 3 && lane == 0) {
+                    cscalT[buf * 2 + 0] = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
+                    cscalT[buf * 2 + 1] = FAC ? a.g_aligned[(int64_t)n * a.g_aligned_stride] : T(0);
+                    cscalI[buf * 2 + 0] = (int)a.ctx.il[n];
+                    cscalI[buf * 2 + 1] = Sn_;
+                }
+                mbar_arrive(&cfull[buf]);        // every lane of the three warps: its own stores are released
+            }
+        }
         if (warp == PW && lane == 0) {
             int n = q_begin / a.tiles_t, tt = q_begin - n * a.tiles_t;     // walked, no per-tile divisions
             int Tn = (q_begin < q_end) ? (int)a.ctx.il[n] : 0;
@@ -200,7 +242,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     }
     cbar();
 
-    int cur_n = -1, nutt = 0;
+    int cur_n = -1, nutt = 0, useq = 0;
     int Tn = 0, Sn = 0;
     T gf = T(0), ga = T(0);
     // narrow mode: this lane's block of the current utterance.  accH: posterior mass that STAYED into position j,
@@ -253,36 +295,41 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
         if (n != cur_n) {
             flush_fac();
             cur_n = n;
-            Tn = (int)a.ctx.il[n];
-            gf = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
-            ga = FAC ? a.g_aligned[(int64_t)n * a.g_aligned_stride] : T(0);
-            if (FAC) {
-                Sn = (int)a.ctx.tl[n];
-                const int64_t *yn = a.y + (int64_t)n * a.y_s0;
-                if (narrow) {
-                    // every warp loads its own copy of the utterance constants: no barrier
+            if (prefetch) {
+                const int buf = useq & 1;
+                mbar_wait(&cfull[buf], (useq >> 1) & 1);
+                gf = cscalT[buf * 2 + 0]; ga = cscalT[buf * 2 + 1];
+                Tn = cscalI[buf * 2 + 0]; Sn = cscalI[buf * 2 + 1];
+                if (FAC) {
+                    const int o = buf * sp + min(lane, nblk - 1) * 8;
+                    const int4 l0 = *reinterpret_cast<const int4 *>(ylab + o), l1 = *reinterpret_cast<const int4 *>(ylab + o + 4);
+                    lab[0] = l0.x; lab[1] = l0.y; lab[2] = l0.z; lab[3] = l0.w; lab[4] = l1.x; lab[5] = l1.y; lab[6] = l1.z; lab[7] = l1.w;
+                    lds8(hh + o, hreg);
+                    lds8(din + o, dreg);
+                    if (lane >= nblk) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int s = lane * 8 + j;
-                        lab[j] = L; hreg[j] = T(0); dreg[j] = T(0);
-                        if (s < Sn) {
-                            lab[j] = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
-                            hreg[j] = a.ctx.fac_hd[(int64_t)n * sp + s];
-                            if (s >= 1) dreg[j] = a.ctx.fac_hd[((int64_t)N + n) * sp + s - 1];
-                        }
+                        for (int j = 0; j < 8; ++j) { lab[j] = L; hreg[j] = T(0); dreg[j] = T(0); }
                     }
                     labm1 = __shfl_up_sync(ASG_FULL_MASK, lab[7], 1);
-                } else {
-                    cbar();                        // the previous utterance's frames are done everywhere
-                    for (int s = tid; s < sp; s += ncons) {
-                        int lb = L;
-                        if (s < Sn) lb = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
-                        ylab[s] = lb;
-                        hh[s] = a.ctx.fac_hd[(int64_t)n * sp + s];
-                        din[s] = (s >= 1) ? a.ctx.fac_hd[((int64_t)N + n) * sp + s - 1] : T(0);
-                    }
-                    cbar();
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&cempty[buf]);      // the constants now live in registers
+                ++useq;
+            } else {
+                Tn = (int)a.ctx.il[n];
+                gf = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
+                ga = FAC ? a.g_aligned[(int64_t)n * a.g_aligned_stride] : T(0);
+                Sn = (int)a.ctx.tl[n];
+                const int64_t *yn = a.y + (int64_t)n * a.y_s0;
+                cbar();                        // the previous utterance's frames are done everywhere
+                for (int s = tid; s < sp; s += ncons) {
+                    int lb = L;
+                    if (s < Sn) lb = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
+                    ylab[s] = lb;
+                    hh[s] = a.ctx.fac_hd[(int64_t)n * sp + s];
+                    din[s] = (s >= 1) ? a.ctx.fac_hd[((int64_t)N + n) * sp + s - 1] : T(0);
+                }
+                cbar();
             }
         }
         const int rows_valid = max(0, min(TBt, Tn - t0));   // frames t0 .. t0+rows_valid-1 are inside the utterance

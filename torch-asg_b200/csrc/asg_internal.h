@@ -1,6 +1,7 @@
 // asg_internal.h -- host/device structs shared between the translation units of libasg_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include "../../include/asg_b200.h"
 
@@ -113,5 +114,6 @@ struct LaunchScope {
     ~LaunchScope();
     int kid_; cudaStream_t st_; int slot_;
 };
+
 
 }  // namespace asg
