@@ -138,6 +138,14 @@ template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile(
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // shared-memory loads through 32-bit shared addresses (no generic->shared conversion in hot loops)
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4f32(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));

@@ -32,6 +32,7 @@ namespace asg {
 constexpr int FB = 8;             // frames per producer batch (4 lanes per frame)
 constexpr int NRAW = 4;           // raw batches in flight (cp.async groups)
 constexpr int RING = NRAW * FB;   // depth of the u ring, in frames
+constexpr int SCAN_CARVEOUT_PCT = 50;   // preferred shared-memory carve-out of both scan kernels (percent of the maximum)
 
 // ---------------------------------------------------------------------------------------------
 // producer: x rows -> u ring.  Shared by the FCC and FAC kernels.
@@ -355,7 +356,6 @@ __device__ __forceinline__ float2 lds_v2(unsigned addr) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
 
 template <int LP, bool BETA>
 __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &sm, int n, int Tn, int lane) {
@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(64, 1) fcc_scan_kernel(const ScanArgs<T> a) {
 template <typename T> struct FacSmemView {
     T *raw;        // [NRAW*FB][lpi]
     T *uring;      // [RING][up]      up = lpi + 4: entries [lpi, up) are the always-zero slots
+    T *pring;      // [RING][sp]      (one float consumer warp only) u by target position, pair-interleaved per block
     T *xval;       // [2][W+1]  boundary mantissas between consumer warps
     int *xexp;     // [2][W+1]
     int *ylab;     // [sp]
@@ -578,12 +579,13 @@ template <typename T> struct FacSmemView {
 };
 
 template <typename T>
-__host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, int lpi, int sp, int W) {
+__host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, int lpi, int sp, int W, bool posring) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return o; };
     const int up = lpi + 4;
     size_t o_raw = take(sizeof(T) * NRAW * FB * up);
     size_t o_uring = take(sizeof(T) * RING * up);
+    size_t o_pring = take(posring ? sizeof(T) * RING * sp : 0);
     size_t o_xval = take(sizeof(T) * 2 * (W + 1));
     size_t o_xexp = take(sizeof(int) * 2 * (W + 1));
     size_t o_ylab = take(sizeof(int) * sp);
@@ -592,7 +594,7 @@ __host__ __device__ inline size_t fac_smem_carve(FacSmemView<T> *v, char *base, 
     size_t o_flags = take(sizeof(int) * 4);
     size_t o_cons = take(sizeof(int) * W);
     if (v) {
-        v->raw = (T *)(base + o_raw); v->uring = (T *)(base + o_uring);
+        v->raw = (T *)(base + o_raw); v->uring = (T *)(base + o_uring); v->pring = posring ? (T *)(base + o_pring) : nullptr;
         v->xval = (T *)(base + o_xval); v->xexp = (int *)(base + o_xexp);
         v->ylab = (int *)(base + o_ylab); v->red = (T *)(base + o_red); v->msum = (double *)(base + o_msum);
         v->flags = (int *)(base + o_flags); v->consumed = (int *)(base + o_cons);
@@ -764,7 +766,7 @@ __device__ __forceinline__ float max8(const float2 (&p)[4]) {
 // One consumer warp (S <= 256).  Lane boundaries need no special cases: shfl_up/down hand the edge lane its OWN
 // value, which a per-lane 0/1 mask turns into "no neighbour".  The boundary value travels UN-normalised, together
 // with the exponent it is expressed in, as soon as it exists -- the shuffle overlaps the normalisation of the step.
-template <bool BETA>
+template <bool BETA, bool VEC>
 __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &sm, int n, int Tn, int Sn, float Rb,
                                  const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int lane) {
     typedef float T;
@@ -786,13 +788,17 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
 
     // pairs: index q holds positions (q, q+4) of this lane's block
     float2 h2[4], d2[4];
+    // u by position: sm.pring (two LDS.128 per step, already pair-interleaved) when the producer fills it, else the
+    // label gather from the u ring (gather mode of the large alphabets: rows are indexed by position there too)
+    constexpr bool vec = VEC;
     unsigned la[8];                                   // shared-memory byte address of u[lab[j]] in ring slot 0
     const unsigned ring0 = smem_u32(sm.uring);
 #pragma unroll
     for (int q = 0; q < 4; ++q) { h2[q] = make_float2(h[q], h[q + 4]); d2[q] = make_float2(dd[q], dd[q + 4]); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) la[j] = ring0 + 4u * (unsigned)lab[j];
-    const unsigned slot_bytes = 4u * (unsigned)up;
+    const unsigned pa = vec ? smem_u32(sm.pring) + 32u * (unsigned)min(lane, nblk - 1) : 0u;
+    const unsigned slot_bytes = vec ? 4u * (unsigned)sp : 4u * (unsigned)up;
 
     float2 P[4];         // alpha: state = feed; beta: state Q
     float2 Wf[4];        // beta: feed = Q o u
@@ -809,12 +815,18 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
         if ((k & (FB - 1)) == 0) {
             if (lane == 0) st_volatile_s32(&sm.consumed[0], k);
             const int need = min(k + FB, Tn);
-            while (ld_volatile_s32(&sm.flags[0]) < need) __nanosleep(20);
+            while (ld_volatile_s32(&sm.flags[vec ? 2 : 0]) < need) __nanosleep(20);
             __threadfence_block();
         }
         float2 u2[4];
+        if (vec) {
+            const float4 ua = lds_v4f32(pa + slot_off), ub = lds_v4f32(pa + slot_off + 16u);
+            u2[0] = make_float2(ua.x, ua.y); u2[1] = make_float2(ua.z, ua.w);
+            u2[2] = make_float2(ub.x, ub.y); u2[3] = make_float2(ub.z, ub.w);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { u2[q].x = lds_f32(la[q] + slot_off); u2[q].y = lds_f32(la[q + 4] + slot_off); }
+            for (int q = 0; q < 4; ++q) { u2[q].x = lds_f32(la[q] + slot_off); u2[q].y = lds_f32(la[q + 4] + slot_off); }
+        }
         slot_off = ((k & (RING - 1)) == RING - 1) ? 0u : slot_off + slot_bytes;
 
         float snd;       // boundary value handed to the neighbour, expressed in 2^Esnd
@@ -934,10 +946,58 @@ template <typename T, bool BETA> struct FacConsumer {
 template <bool BETA> struct FacConsumer<float, BETA> {
     __device__ static void run(const ScanArgs<float> &a, FacSmemView<float> &sm, int W, int n, int Tn, int Sn, float Rb,
                                const float (&h)[ASG_BLK], const float (&dd)[ASG_BLK], const int (&lab)[ASG_BLK], int warp, int lane) {
-        if (W == 1) fac_consumer_f32<BETA>(a, sm, n, Tn, Sn, Rb, h, dd, lab, lane);
+        if (W == 1 && sm.pring) fac_consumer_f32<BETA, true>(a, sm, n, Tn, Sn, Rb, h, dd, lab, lane);
+        else if (W == 1) fac_consumer_f32<BETA, false>(a, sm, n, Tn, Sn, Rb, h, dd, lab, lane);
         else fac_consumer<float, BETA>(a, sm, W, n, Tn, Sn, Rb, h, dd, lab, warp, lane);
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// FAC, one float consumer warp: a third warp lays every published u row out BY TARGET POSITION,
+//   pring[slot][8b + {0,2,4,6,1,3,5,7}[j]] = u[y_{8b+j}],
+// so the consumer reads its block of eight as two LDS.128 that land directly in its packed (j, j+4) register
+// pairs, instead of eight scalar gathers with their address arithmetic on the serial chain.  The gather costs
+// ~70 instructions per frame: too much to add to the producer warp (it would become the slowest of the three).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void fac_gatherer(FacSmemView<T> &sm, int up, int pp, int Tn, int lane) {
+    unsigned psrc[8], pdst[8];                   // byte offsets inside a u row / a position row of this lane's 8 positions
+    unsigned pvalid = 0;
+    const unsigned ur0 = smem_u32(sm.uring), pr0 = smem_u32(sm.pring);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int sx = lane + 32 * i, j = sx & 7;
+        psrc[i] = pdst[i] = 0;
+        if (sx < pp) {
+            pvalid |= 1u << i;
+            psrc[i] = (unsigned)sizeof(T) * (unsigned)(sm.ylab[sx] >= 0 ? sm.ylab[sx] : up - 1);
+            pdst[i] = (unsigned)sizeof(T) * (unsigned)((sx & ~7) + ((j & 3) << 1) + (j >> 2));
+        }
+    }
+    const int nb = (Tn + FB - 1) / FB;
+    for (int b = 0; b < nb; ++b) {
+        const int kb = b * FB, hi = min(kb + FB, Tn), nf = hi - kb;
+        // the u rows of the batch are published, and the position rows they overwrite have been consumed
+        while (ld_volatile_s32(&sm.flags[0]) < hi || ld_volatile_s32(&sm.consumed[0]) < hi - RING) __nanosleep(20);
+        __threadfence_block();
+        const unsigned slot0 = (unsigned)(kb % RING);          // FB divides RING: a batch never wraps
+        for (int ff = 0; ff < nf; ++ff) {
+            const unsigned ua = ur0 + (slot0 + ff) * (unsigned)(up * sizeof(T));
+            const unsigned pa = pr0 + (slot0 + ff) * (unsigned)(pp * sizeof(T));
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = lds_f32(ua + psrc[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (pvalid & (1u << i)) sts_f32(pa + pdst[i], v[i]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            st_volatile_s32(&sm.flags[2], hi);
+        }
+    }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int W) {
@@ -947,18 +1007,21 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
     const int sp = (int)a.ctx.sp;
     const int lpi = a.fmax ? sp : (int)a.ctx.lpi;     // entries per ring row: all labels, or (large alphabets) the target positions
     const int up = lpi + 4;
-    fac_smem_carve<T>(&sm, smem_raw, lpi, sp, W);
+    const bool posring = W == 1 && sizeof(T) == 4 && a.fmax == nullptr;
+    fac_smem_carve<T>(&sm, smem_raw, lpi, sp, W, posring);
     const int n = blockIdx.x;
     const int dir = blockIdx.y == 0 ? a.dir0 : a.dir1;
+    // roles by warp index: [0, W) consumers, W producer, W+1 position-ring warp (rotating the roles so that the FCC and
+    // FAC consumers of two CTAs sharing an SM sit in different warp slots was measured: 241-246 us vs 222 us as is)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nthreads = 32 * W + 32;
+    const int nthreads = 32 * W + 32 + (posring ? 32 : 0);
 
     int Tn = a.il ? (int)a.il[n] : a.d.T;
     Tn = max(0, min(Tn, a.d.T));
     int Sn = a.tl ? (int)a.tl[n] : S;
     Sn = max(1, min(Sn, S));
 
-    if (threadIdx.x == 0) { sm.flags[0] = 0; sm.flags[1] = 0; }
+    if (threadIdx.x == 0) { sm.flags[0] = 0; sm.flags[1] = 0; sm.flags[2] = 0; }
     if (threadIdx.x < W) sm.consumed[threadIdx.x] = 0;
     const int64_t *yn = a.y + (int64_t)n * a.y_s0;
     for (int s = threadIdx.x; s < sp; s += nthreads) {
@@ -998,6 +1061,10 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
     for (int q = 0; q < W; ++q) Rb = tmax(Rb, sm.red[q]);
     if (!(Rb > ninf)) Rb = T(0);
 
+    if (warp == W + 1) {                 // position-ring warp (only launched with posring)
+        fac_gatherer<T>(sm, up, sp, Tn, lane);
+        return;
+    }
     if (!consumer) {
         auto cons = [&]() {
             int c = 0x7fffffff;
@@ -1074,6 +1141,9 @@ static cudaError_t launch_fcc_lp(const ScanArgs<T> &a, int ndirs, cudaStream_t s
         const size_t bytes = sizeof(FccSmem<T, LP>);
         cudaError_t e = cudaFuncSetAttribute(fcc_scan_kernel<T, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
+        // the FCC and FAC scan kernels run side by side on the same SMs: both ask for the same L1/shared split, or the
+        // second one can only use SMs the first has left empty (an SM changes its carve-out only when idle)
+        cudaFuncSetAttribute(fcc_scan_kernel<T, LP>, cudaFuncAttributePreferredSharedMemoryCarveout, SCAN_CARVEOUT_PCT);
         LaunchScope ls(K_FCC_SCAN, st);
         fcc_scan_kernel<T, LP><<<grid, 64, bytes, st>>>(a);
     }
@@ -1098,14 +1168,17 @@ template <typename T> static cudaError_t launch_fac(const ScanArgs<T> &a, int nd
     int W = 1;
     while (W * 32 < lanes) W <<= 1;
     if (W > 16) return cudaErrorInvalidValue;
-    const size_t bytes = fac_smem_carve<T>(nullptr, nullptr, a.fmax ? (int)a.ctx.sp : (int)a.ctx.lpi, (int)a.ctx.sp, W);
+    const size_t bytes = fac_smem_carve<T>(nullptr, nullptr, a.fmax ? (int)a.ctx.sp : (int)a.ctx.lpi, (int)a.ctx.sp, W,
+                                           W == 1 && sizeof(T) == 4 && a.fmax == nullptr);
     if (bytes > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(fac_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     dim3 grid(a.d.N, ndirs);
     {
+        cudaFuncSetAttribute(fac_scan_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, SCAN_CARVEOUT_PCT);
         LaunchScope ls(K_FAC_SCAN, st);
-        fac_scan_kernel<T><<<grid, 32 * W + 32, bytes, st>>>(a, W);
+        const bool posring = W == 1 && sizeof(T) == 4 && a.fmax == nullptr;
+        fac_scan_kernel<T><<<grid, 32 * W + 32 + (posring ? 32 : 0), bytes, st>>>(a, W);
     }
     return cudaGetLastError();
 }
