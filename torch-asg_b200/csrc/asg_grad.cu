@@ -13,7 +13,7 @@
 // alpha[t-1] and u*beta[t] on the fly.
 //
 // Structure.  tile = (utterance n, TB consecutive frames).  State is utterance-major, so a tile of every state
-// array is ONE contiguous chunk: a producer warp fetches it with 8 bulk (TMA) copies (cp.async.bulk -> UBLKCP)
+// array is ONE contiguous chunk: the producer fetches it with one bulk (TMA) copy (cp.async.bulk -> UBLKCP)
 // into an NS-stage shared-memory ring guarded by mbarriers.  Each of the NW consumer warps then owns whole
 // frames of the tile -- one warp per (utterance, frame) slice, lane = one 8-position block of the target /
 // one or two labels -- and does everything for its frame in registers with no block-wide barrier:
@@ -286,11 +286,17 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
         ++nutt;
     };
 
-    int it = 0;
-    for (int q = q_begin; q < q_end; ++q, ++it) {
-        const int stage = it % NS, use = it / NS;
-        const int n = q / a.tiles_t;
-        const int t0 = (q % a.tiles_t) * TB;
+    // byte offsets of this lane's slices inside a frame record (idle lanes re-read the last block, weight 0)
+    const int lbk = min(lane, max(nblk, 1) - 1);
+    const int offA = a.ctx.o_fa + lbk * 8 * (int)sizeof(T), offB = a.ctx.o_fb + lbk * 8 * (int)sizeof(T);
+    const int offEa = a.ctx.o_ea + lbk * 4, offEb = a.ctx.o_eb + lbk * 4;
+    const int offCa = a.ctx.o_ca + lane * (int)sizeof(T), offCb = a.ctx.o_cb + lane * (int)sizeof(T);
+    const int offCw = a.ctx.o_cw + ib * RI * (int)sizeof(T), offPw = a.ctx.o_ca + jb * CJ * (int)sizeof(T);
+    // (utterance, tile-in-utterance, ring stage, ring pass) are walked: no per-tile divisions
+    int wn = q_begin / a.tiles_t, wt = q_begin - wn * a.tiles_t, stage = 0, use = 0;
+    for (int q = q_begin; q < q_end; ++q) {
+        const int n = wn;
+        const int t0 = wt * TB;
         const int TBt = min(TB, Tt - t0);         // frames in this tile
         if (n != cur_n) {
             flush_fac();
@@ -353,26 +359,25 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
         if (narrow && TB == 2 * NW && rows_valid == TB && t0 > 0 && !a.dry) {
             const int ra = 1 + warp, rb = 1 + warp + NW;
             const int rr[2] = {ra, rb};
-            const int lb8 = min(lane, nblk - 1) * 8;          // idle lanes re-read the last block (weight 0)
-            const int le = min(lane, nblk - 1);
             const bool act = lane < nblk;
+            const char *rowp[2] = {srec + (size_t)ra * R, srec + (size_t)rb * R};      // this warp's two frame records
             T bv[2][8];
             if (FAC) {
                 T av[2][8];
                 int ea[2], eb[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    lds8(A_(rr[u]) + lb8, av[u]);
-                    lds8(B_(rr[u]) + lb8, bv[u]);
-                    ea[u] = Ea_(rr[u])[le];
-                    eb[u] = Eb_(rr[u])[le];
+                    lds8((const T *)(rowp[u] + offA), av[u]);
+                    lds8((const T *)(rowp[u] + offB), bv[u]);
+                    ea[u] = *(const int *)(rowp[u] + offEa);
+                    eb[u] = *(const int *)(rowp[u] + offEb);
                 }
                 T pv[2][8];
                 int ep[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    lds8(A_(rr[u] - 1) + lb8, pv[u]);
-                    ep[u] = Ea_(rr[u] - 1)[le];
+                    lds8((const T *)(rowp[u] - R + offA), pv[u]);
+                    ep[u] = *(const int *)(rowp[u] - R + offEa);
                 }
                 T ps[2];
                 int c[2];
@@ -431,8 +436,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         al0[u] = al1[u] = be0[u] = be1[u] = T(0);
-                        if (lane < lpi) { al0[u] = Fa_(rr[u])[lane]; be0[u] = Fb_(rr[u])[lane]; }
-                        if (LP > 32 && lane + 32 < lpi) { al1[u] = Fa_(rr[u])[lane + 32]; be1[u] = Fb_(rr[u])[lane + 32]; }
+                        if (lane < lpi) { al0[u] = *(const T *)(rowp[u] + offCa); be0[u] = *(const T *)(rowp[u] + offCb); }
+                        if (LP > 32 && lane + 32 < lpi) { al1[u] = *(const T *)(rowp[u] + offCa + 32 * (int)sizeof(T)); be1[u] = *(const T *)(rowp[u] + offCb + 32 * (int)sizeof(T)); }
                         g0[u] = al0[u] * be0[u]; g1[u] = al1[u] * be1[u];
                     }
                     T z0 = g0[0] + g1[0], z1 = g0[1] + g1[1];
@@ -447,12 +452,12 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     g0[u] *= inv[u]; g1[u] *= inv[u];
-                    const T winv = inv[u] * Sc_(rr[u]);
+                    const T winv = inv[u] * *(const T *)(rowp[u] + a.ctx.o_sc);
                     T wv[RI], pw[CJ];
 #pragma unroll
-                    for (int i = 0; i < RI; ++i) wv[i] = Fw_(rr[u])[ib * RI + i] * winv;
+                    for (int i = 0; i < RI; ++i) wv[i] = ((const T *)(rowp[u] + offCw))[i] * winv;
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) pw[j] = Fa_(rr[u] - 1)[jb * CJ + j];
+                    for (int j = 0; j < CJ; ++j) pw[j] = ((const T *)(rowp[u] - R + offPw))[j];
 #pragma unroll
                     for (int i = 0; i < RI; ++i)
 #pragma unroll
@@ -622,6 +627,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
         // release the stage (read-only for the consumers)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == NS) { stage = 0; ++use; }
+        if (++wt == a.tiles_t) { wt = 0; ++wn; }
     }
     flush_fac();
     cbar();
