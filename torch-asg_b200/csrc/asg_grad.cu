@@ -61,6 +61,19 @@ template <> struct Fix<double> {
     __device__ __forceinline__ static double edge_unfix(unsigned long long q) { return (double)(long long)q * (1.0 / 274877906944.0); }
 };
 
+// pairs of accumulators: float pairs use the packed two-FMA instruction of sm_100 (FFMA2), double pairs are two FMAs
+template <typename T> struct Pk;
+template <> struct Pk<float> {
+    typedef float2 v2;
+    __device__ __forceinline__ static v2 mk(float a, float b) { return make_float2(a, b); }
+    __device__ __forceinline__ static v2 fma2(v2 a, v2 b, v2 c) { return __ffma2_rn(a, b, c); }
+};
+template <> struct Pk<double> {
+    typedef double2 v2;
+    __device__ __forceinline__ static v2 mk(double a, double b) { return make_double2(a, b); }
+    __device__ __forceinline__ static v2 fma2(v2 a, v2 b, v2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+};
+
 // approximate (float) / exact (double) quotient for the edge posteriors
 __device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
@@ -224,11 +237,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     // FCC: per-lane register slice of this warp's G: rows ib*RI.., columns jb*CJ..
     constexpr int RI = LP / 8, CJ = LP / 4;
     const int ib = lane >> 2, jb = lane & 3;
-    T G[RI][CJ];
+    typedef typename Pk<T>::v2 V2;
+    constexpr int CJ2 = CJ / 2;                    // LP is a multiple of 8: CJ is even
+    V2 G[RI][CJ2];                                 // columns (2c, 2c+1) of the slice travel as one pair
 #pragma unroll
     for (int i = 0; i < RI; ++i)
 #pragma unroll
-        for (int j = 0; j < CJ; ++j) G[i][j] = T(0);
+        for (int j = 0; j < CJ2; ++j) G[i][j] = Pk<T>::mk(T(0), T(0));
 
     unsigned long long *galfix = (unsigned long long *)(smem_raw + mp.o_galfix);     // [2][L*L] fixed-point edge sums
     for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
@@ -453,15 +468,18 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 for (int u = 0; u < 2; ++u) {
                     g0[u] *= inv[u]; g1[u] *= inv[u];
                     const T winv = inv[u] * *(const T *)(rowp[u] + a.ctx.o_sc);
-                    T wv[RI], pw[CJ];
+                    T wv[RI];
+                    V2 pw[CJ2];
 #pragma unroll
                     for (int i = 0; i < RI; ++i) wv[i] = ((const T *)(rowp[u] + offCw))[i] * winv;
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) pw[j] = ((const T *)(rowp[u] - R + offPw))[j];
+                    for (int j = 0; j < CJ2; ++j) pw[j] = ((const V2 *)(rowp[u] - R + offPw))[j];
 #pragma unroll
-                    for (int i = 0; i < RI; ++i)
+                    for (int i = 0; i < RI; ++i) {
+                        const V2 w2 = Pk<T>::mk(wv[i], wv[i]);
 #pragma unroll
-                        for (int j = 0; j < CJ; ++j) G[i][j] = fma(wv[i], pw[j], G[i][j]);
+                        for (int j = 0; j < CJ2; ++j) G[i][j] = Pk<T>::fma2(w2, pw[j], G[i][j]);
+                    }
                 }
             }
 #pragma unroll
@@ -604,15 +622,18 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 g0 *= inv; g1 *= inv;
                 if (t >= 1) {                                  // no incoming edge at frame 0
                     const T winv = inv * Sc_(r);
-                    T wv[RI], pv[CJ];
+                    T wv[RI];
+                    V2 pv[CJ2];
 #pragma unroll
                     for (int i = 0; i < RI; ++i) wv[i] = Fw_(r)[ib * RI + i] * winv;
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) pv[j] = Fa_(r - 1)[jb * CJ + j];
+                    for (int j = 0; j < CJ2; ++j) pv[j] = ((const V2 *)(Fa_(r - 1) + jb * CJ))[j];
 #pragma unroll
-                    for (int i = 0; i < RI; ++i)
+                    for (int i = 0; i < RI; ++i) {
+                        const V2 w2 = Pk<T>::mk(wv[i], wv[i]);
 #pragma unroll
-                        for (int j = 0; j < CJ; ++j) G[i][j] = fma(wv[i], pv[j], G[i][j]);
+                        for (int j = 0; j < CJ2; ++j) G[i][j] = Pk<T>::fma2(w2, pv[j], G[i][j]);
+                    }
                 }
             }
             if (FAC) {
@@ -645,7 +666,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
             for (int j = 0; j < CJ; ++j) {
                 const int gi = ib * RI + i, gj = jb * CJ + j;
-                if (gi < L && gj < L) slice[gi * L + gj] = G[i][j];
+                if (gi < L && gj < L) slice[gi * L + gj] = (j & 1) ? G[i][j >> 1].y : G[i][j >> 1].x;
             }
         cbar();
         for (int e = tid; e < L * L; e += ncons) {
@@ -661,7 +682,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                     for (int j = 0; j < CJ; ++j) {
                         const int gi = ib * RI + i, gj = jb * CJ + j;
-                        if (gi < L && gj < L) Gf[gi * L + gj] += G[i][j];
+                        if (gi < L && gj < L) Gf[gi * L + gj] += (j & 1) ? G[i][j >> 1].y : G[i][j >> 1].x;
                     }
             }
             cbar();
