@@ -259,6 +259,61 @@ def test_c_abi_host_loss(npdt, tol):
     assert rel(loss2, ref["loss"], 1.0) <= tol
 
 
+def test_c_abi_contexts_in_flight():
+    """asg_host_submit / asg_host_wait: several host contexts in flight at once (what bench.py's e2e leg does), each with
+    its own inputs, submitted from two host threads.  Every context must return exactly what a lone asg_host_loss
+    call returns for the same inputs (bit-identical: the kernels are deterministic), i.e. contexts share nothing."""
+    import threading
+    lib = _lib()
+    T, N, L, S = 90, 6, 31, 20
+    i64 = ctypes.c_int64
+    p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    cases = []
+    for c in range(6):
+        r = np.random.default_rng(100 + c)
+        x = r.standard_normal((T, N, L)).astype(np.float32)
+        A = (0.5 * r.standard_normal((L, L))).astype(np.float32)
+        y = r.integers(0, L, (N, S)).astype(np.int64)
+        tl = r.integers(1, S + 1, N).astype(np.int64)
+        il = np.array([r.integers(max(tl[n], T // 2), T + 1) for n in range(N)], dtype=np.int64)
+        g = r.uniform(0.5, 1.5, N).astype(np.float32)
+        cases.append((x, A, y, il, tl, g))
+    alone = [_host_loss(lib, *c) for c in cases]
+    ctxs, outs = [], []
+    for _ in cases:
+        h = ctypes.c_void_p()
+        assert lib.asg_host_create(0, 0, i64(T), i64(N), i64(L), i64(S), ctypes.byref(h)) == 0, lib.asg_last_error()
+        ctxs.append(h)
+        outs.append((np.empty(N, np.float32), np.empty((T, N, L), np.float32), np.empty((L, L), np.float32)))
+    errors = []
+
+    def worker(ids):
+        for rep in range(3):                      # resubmitting a context reuses its device buffers
+            for i in ids:
+                x, A, y, il, tl, g = cases[i]
+                loss, gx, gA = outs[i]
+                if lib.asg_host_submit(ctxs[i], p(x), p(A), p(y), p(il), p(tl), p(g), i64(T), i64(N), i64(L), i64(S),
+                                       p(loss), p(gx), p(gA)) != 0:
+                    errors.append(lib.asg_last_error())
+            for i in ids:
+                if lib.asg_host_wait(ctxs[i]) != 0:
+                    errors.append(lib.asg_last_error())
+
+    threads = [threading.Thread(target=worker, args=(ids,)) for ids in ([0, 2, 4], [1, 3, 5])]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for h in ctxs:
+        lib.asg_host_destroy(h)
+    for (loss, gx, gA), (loss0, gx0, gA0) in zip(outs, alone):
+        assert np.array_equal(loss, loss0) and np.array_equal(gx, gx0) and np.array_equal(gA, gA0)
+    ref = O.asg_loss(cases[3][0].astype(np.float64), cases[3][2], cases[3][1].astype(np.float64), cases[3][3], cases[3][4],
+                     cases[3][5].astype(np.float64))
+    assert rel(outs[3][0], ref["loss"], 1.0) <= TOL32 and rel(outs[3][1], ref["gx"]) <= TOL32 and rel(outs[3][2], ref["gA"]) <= TOL32
+
+
 def test_c_abi_errors():
     lib = _lib()
     lay = (ctypes.c_char * 256)()
