@@ -435,6 +435,37 @@ def test_sharded_equals_whole(surf):
     assert np.abs(parts[0][2] + parts[1][2] - gA).max() < 1e-10
 
 
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_sharded_direct_step_matches_public_api(reduction):
+    """sharded_asg_step drives the native boundary directly (no autograd graph).  On one rank it must give exactly
+    what ASGLoss(...)(...) + backward() gives: loss, input gradient (leaf and non-leaf inputs), transition gradient."""
+    import torch_asg
+    from torch_asg.sharded import sharded_asg_step, FusedAllReduce
+    T, N, L, S = 120, 6, 40, 30
+    x, A, y, il, tl, _ = _synthetic(T, N, L, S, seed=9, varlen=True)
+    dev = "cuda"
+    crit = torch_asg.ASGLoss(L, reduction=reduction).to(dev).double()
+    with torch.no_grad():
+        crit.transition.copy_(A.to(dev))
+    yd, ild, tld = y.to(dev), il.to(dev), tl.to(dev)
+    xa = x.to(dev).requires_grad_()
+    loss_a = crit(xa, yd, ild, tld)
+    loss_a.backward()
+    gA_a = crit.transition.grad.clone()
+    crit.transition.grad = None
+    fused = FusedAllReduce(crit)
+    xb = x.to(dev).requires_grad_()
+    loss_b = sharded_asg_step(crit, xb, yd, ild, tld, fused=fused)
+    assert torch.equal(loss_b, loss_a.detach()) or abs(float(loss_b) - float(loss_a)) <= 1e-12 * abs(float(loss_a))
+    assert torch.equal(xb.grad, xa.grad)
+    assert torch.equal(crit.transition.grad, gA_a)
+    # non-leaf inputs: the gradient is propagated into the graph that produced them
+    leaf = x.to(dev).requires_grad_()
+    loss_c = sharded_asg_step(crit, leaf * 1.0, yd, ild, tld, fused=fused)
+    assert torch.equal(leaf.grad, xa.grad) and torch.equal(crit.transition.grad, gA_a)
+    assert abs(float(loss_c) - float(loss_a)) <= 1e-12 * abs(float(loss_a))
+
+
 # ----------------------------------------------------------------------------------------------
 # large alphabets (L > 64): E no longer fits on chip -- separate kernels, same records, same ABI
 # ----------------------------------------------------------------------------------------------

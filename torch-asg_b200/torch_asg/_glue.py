@@ -116,6 +116,8 @@ def bind_native(native):
         ('mean' over the batch -- the default --, 'sum', anything else: none).
         Reference: ``asg.py:100-142``; option semantics ``README.md:84-94``."""
 
+        _native = native          # the bound native module (torch_asg.sharded calls it directly)
+
         def __init__(self, num_labels, reduction='mean', forward_only=False,
                      gpu_no_stream_impl=False):
             super().__init__()

@@ -83,12 +83,48 @@ class FusedAllReduce:
             t = self._seeds[scale] = torch.full((), scale, dtype=self.buf.dtype, device=self.buf.device)
         return t
 
+    def seed_vectors(self, n, scale):
+        """Per-utterance upstream gradients ``(+scale, -scale)`` of (FCC score, FAC score), cached."""
+        key = (n, scale)
+        t = self._seeds.get(key)
+        if t is None:
+            up = torch.full((n,), scale, dtype=self.buf.dtype, device=self.buf.device)
+            t = self._seeds[key] = (up, -up)
+        return t
+
     def reduce(self, loss_sum, count):
         self.loss_slot.copy_(loss_sum.reshape(1))
         self.count_slot.fill_(count)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
         return self.loss_out, self.count_out
+
+
+def _direct_step(criterion, native, inputs, targets, input_lengths, target_lengths, scale, fused):
+    """Forward + backward of this rank's shard straight through the native boundary (no autograd graph): the two
+    native calls, one loss sum and one copy of the transition gradient into the fused buffer.  The autograd engine
+    costs ~0.1 ms of host time per step (a thread hand-off and four graph nodes); with several ranks per box the step
+    was bound by host issue time, not by the GPU, so the sharded path skips it.  ``inputs`` gets its gradient the way
+    autograd would deliver it: accumulated into ``.grad`` for a leaf, propagated with ``backward`` otherwise."""
+    targets, input_lengths, target_lengths = criterion._lengths(inputs, targets, input_lengths, target_lengths)
+    T, N, L = inputs.shape
+    S = targets.shape[1]
+    x = inputs.detach()
+    A = criterion.transition.detach()
+    full, aligned, g_full, g_aligned, c_full, c_aligned = native.fast_asg_gpu_forward(
+        x, targets, A, input_lengths, target_lengths, T, N, L, S)
+    local_sum = (full - aligned).sum()
+    up, down = fused.seed_vectors(N, scale)
+    grad_A, grad_x = native.fast_asg_gpu_backward(up, down, g_full, g_aligned, c_full, c_aligned, targets,
+                                                  input_lengths, target_lengths, T, N, L, S)
+    fused.grad_view.copy_(grad_A)
+    criterion.transition.grad = fused.grad_view
+    if inputs.requires_grad:
+        if inputs.grad_fn is None:
+            inputs.grad = grad_x if inputs.grad is None else inputs.grad + grad_x
+        else:
+            inputs.backward(grad_x)
+    return local_sum
 
 
 def sharded_asg_step(criterion, inputs, targets, input_lengths=None, target_lengths=None, group=None,
@@ -109,15 +145,23 @@ def sharded_asg_step(criterion, inputs, targets, input_lengths=None, target_leng
     reduction = criterion.reduction
     if fused is None:
         fused = FusedAllReduce(criterion, group)
-    fused.prepare(criterion)
-    criterion.reduction = 'sum'
-    try:
-        local_sum = criterion(inputs, targets, input_lengths, target_lengths)
-    finally:
-        criterion.reduction = reduction
     scale = 1.0 / global_batch if reduction == 'mean' else 1.0
-    local_sum.backward(fused.seed(scale))        # seeds the backward with the global scale: no extra graph node
-    loss_sum, count = fused.reduce(local_sum.detach(), float(n_local))
+    native = getattr(type(criterion), "_native", None)
+    direct = (native is not None and hasattr(native, "fast_asg_gpu_backward") and inputs.is_cuda and criterion.training
+              and not getattr(criterion, "forward_only", False) and not getattr(criterion, "gpu_no_stream_impl", False)
+              and reduction in ('mean', 'sum'))
+    if direct:
+        local_sum = _direct_step(criterion, native, inputs, targets, input_lengths, target_lengths, scale, fused)
+    else:
+        fused.prepare(criterion)
+        criterion.reduction = 'sum'
+        try:
+            local_sum = criterion(inputs, targets, input_lengths, target_lengths)
+        finally:
+            criterion.reduction = reduction
+        local_sum.backward(fused.seed(scale))        # seeds the backward with the global scale: no extra graph node
+        local_sum = local_sum.detach()
+    loss_sum, count = fused.reduce(local_sum, float(n_local))
     if reduction == 'mean':
         return loss_sum / count
     return loss_sum
