@@ -435,6 +435,28 @@ def test_sharded_equals_whole(surf):
     assert np.abs(parts[0][2] + parts[1][2] - gA).max() < 1e-10
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float64, TOL64)])
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (2, 3, 1, 2), (7, 2, 8, 3), (9, 3, 9, 4), (12, 2, 64, 5), (11, 5, 65, 4),
+                                   (300, 2, 33, 257), (40, 3, 24, 40), (33, 1, 200, 9)])
+def test_shape_edges(surf, shape, dtype, tol):
+    """Boundaries of the kernel families against the oracle: L = 1, L at the template steps (8/9), L = 64 | 65 (register-
+    resident E | large-alphabet path), S = 257 (two FAC consumer warps, the wide gradient path), S = T, N = 1."""
+    T, N, L, S = shape
+    r = np.random.default_rng(1000 + T + 7 * L + 13 * S)
+    x = r.standard_normal((T, N, L))
+    A = 0.5 * r.standard_normal((L, L))
+    y = r.integers(0, L, (N, S))
+    tl = r.integers(1, S + 1, N)
+    il = np.array([r.integers(min(T, max(tl[n], (T + 1) // 2)), T + 1) for n in range(N)])
+    tl = np.minimum(tl, il)
+    g = r.uniform(0.5, 1.5, N)
+    ref = O.asg_loss(x, y, A, il, tl, g)
+    o = run_surface(surf, {"x": x, "y": y, "A": A, "il": il, "tl": tl, "g": g}, dtype, "fast")
+    for k, v in o.items():
+        floor = 1.0 if k in ("loss", "full", "aligned") else 1e-30
+        assert rel(v, ref[k], floor) <= tol, (shape, k, rel(v, ref[k], floor))
+
+
 @pytest.mark.parametrize("reduction", ["mean", "sum"])
 def test_sharded_direct_step_matches_public_api(reduction):
     """sharded_asg_step drives the native boundary directly (no autograd graph).  On one rank it must give exactly
