@@ -21,9 +21,11 @@
 //   warp's private fixed-point bins (integer shared-memory atomics: order-independent, so deterministic),
 //   edge posteriors into per-lane register accumulators, FCC posterior, the FCC transition-gradient outer
 //   product into a per-lane register slice of G, and the one coalesced store of the grad_x row.
-// Warps only meet at utterance boundaries (to flush the per-position edge sums through a label CSR into the
-// CTA's L x L matrix, fixed order) and at the end.  Every reduction has a fixed order or is integer:
-// results are run-to-run deterministic.
+// Each warp has two frames in flight (their dependency chains interleave in one instruction stream).  Warps only
+// meet at utterance boundaries (the per-position edge sums go, as 64-bit fixed point, into the CTA's L x L edge
+// matrix) and at the end (G slices parked in the idle tile ring, added in warp order).  Three helper warps in the
+// producer's warpgroup stage the next utterance's labels / h / d / scalars in shared memory one utterance ahead.
+// Every reduction has a fixed order or is integer: results are run-to-run deterministic.
 #include <climits>
 #include <cstdlib>
 #include "asg_common.cuh"
