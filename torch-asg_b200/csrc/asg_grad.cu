@@ -125,6 +125,33 @@ __device__ __forceinline__ void lds8(const double *p, double (&v)[8]) {
     }
 }
 
+// Eight consecutive elements per lane at a 32-byte lane pitch make every 128-bit shared-memory load a 2-way bank
+// conflict (lanes l and l+4 of a quarter-warp hit the same banks).  Lanes with bit 2 set therefore fetch their two halves
+// in the opposite order (sw = 4): the load is conflict-free, and such a lane simply keeps its block PERMUTED in
+// registers -- register r holds position r ^ 4.  Everything per position is loaded the same way (states, labels, h, d),
+// so the element-wise arithmetic never notices; only the three places that need a neighbour do (prev8, last8).
+__device__ __forceinline__ void lds8sw(const float *p, int sw, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p + sw);
+    const float4 b = *reinterpret_cast<const float4 *>(p + (4 - sw));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8sw(const double *p, int sw, double (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const double2 a = *(reinterpret_cast<const double2 *>(p + sw) + q);
+        const double2 b = *(reinterpret_cast<const double2 *>(p + (4 - sw)) + q);
+        v[2 * q] = a.x; v[2 * q + 1] = a.y; v[4 + 2 * q] = b.x; v[4 + 2 * q + 1] = b.y;
+    }
+}
+// value at the position before the one register j holds (`left` = the previous lane's last position)
+template <typename V> __device__ __forceinline__ V prev8(const V (&v)[8], int j, bool fl, V left) {
+    if (j == 0) return fl ? v[7] : left;
+    if (j == 4) return fl ? left : v[3];
+    return v[j - 1];
+}
+// value at the lane's last position (7)
+template <typename V> __device__ __forceinline__ V last8(const V (&v)[8], bool fl) { return fl ? v[3] : v[7]; }
+
 template <typename T, int LP, bool FCC, bool FAC>
 __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(const GradArgs<T> a) {
     extern __shared__ __align__(128) char smem_raw[];
@@ -234,6 +261,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     // =========================== consumer warps =====================================================
     auto cbar = [&]() { named_bar_sync(1, ncons); };
     const bool narrow = nblk <= 32;                // one 8-position block per lane: everything stays in registers
+    const bool fl = (lane >> 2) & 1;               // this lane keeps its 8-position block permuted (see lds8sw)
+    const int sw = fl ? 4 : 0;
     typedef Fix<T> FX;
 
     // FCC: per-lane register slice of this warp's G: rows ib*RI.., columns jb*CJ..
@@ -280,9 +309,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (lab[j] < L) {
-                        const int prevlab = j ? lab[j ? j - 1 : 0] : labm1;
+                        const int prevlab = prev8(lab, j, fl, labm1);
                         atomicAdd(&gfix[lab[j] * L + lab[j]], FX::edge_fix(accH[j]));
-                        if (lane * 8 + j >= 1) atomicAdd(&gfix[lab[j] * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
+                        if (lane * 8 + (j ^ sw) >= 1) atomicAdd(&gfix[lab[j] * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
                     }
                     accH[j] = accQ[j] = T(0);
                 }
@@ -325,15 +354,15 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 Tn = cscalI[buf * 2 + 0]; Sn = cscalI[buf * 2 + 1];
                 if (FAC) {
                     const int o = buf * sp + min(lane, nblk - 1) * 8;
-                    const int4 l0 = *reinterpret_cast<const int4 *>(ylab + o), l1 = *reinterpret_cast<const int4 *>(ylab + o + 4);
+                    const int4 l0 = *reinterpret_cast<const int4 *>(ylab + o + sw), l1 = *reinterpret_cast<const int4 *>(ylab + o + 4 - sw);
                     lab[0] = l0.x; lab[1] = l0.y; lab[2] = l0.z; lab[3] = l0.w; lab[4] = l1.x; lab[5] = l1.y; lab[6] = l1.z; lab[7] = l1.w;
-                    lds8(hh + o, hreg);
-                    lds8(din + o, dreg);
+                    lds8sw(hh + o, sw, hreg);
+                    lds8sw(din + o, sw, dreg);
                     if (lane >= nblk) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { lab[j] = L; hreg[j] = T(0); dreg[j] = T(0); }
                     }
-                    labm1 = __shfl_up_sync(ASG_FULL_MASK, lab[7], 1);
+                    labm1 = __shfl_up_sync(ASG_FULL_MASK, last8(lab, fl), 1);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&cempty[buf]);      // the constants now live in registers
@@ -384,8 +413,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 int ea[2], eb[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    lds8((const T *)(rowp[u] + offA), av[u]);
-                    lds8((const T *)(rowp[u] + offB), bv[u]);
+                    lds8sw((const T *)(rowp[u] + offA), sw, av[u]);
+                    lds8sw((const T *)(rowp[u] + offB), sw, bv[u]);
                     ea[u] = *(const int *)(rowp[u] + offEa);
                     eb[u] = *(const int *)(rowp[u] + offEb);
                 }
@@ -393,7 +422,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 int ep[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    lds8((const T *)(rowp[u] - R + offA), pv[u]);
+                    lds8sw((const T *)(rowp[u] - R + offA), sw, pv[u]);
                     ep[u] = *(const int *)(rowp[u] - R + offEa);
                 }
                 T ps[2];
@@ -431,13 +460,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    T left = __shfl_up_sync(ASG_FULL_MASK, pv[u][7], 1);
+                    T left = __shfl_up_sync(ASG_FULL_MASK, last8(pv[u], fl), 1);
                     const int el = __shfl_up_sync(ASG_FULL_MASK, ep[u], 1);
                     left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep[u], Num<T>::kMaxShift - 8));
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const T stay = hreg[j] * pv[u][j];
-                        const T den = fma(dreg[j], j ? pv[u][j ? j - 1 : 0] : left, stay);
+                        const T den = fma(dreg[j], prev8(pv[u], j, fl, left), stay);
                         const T fs = fast_div(stay, tmax(den, Num<T>::tiny()));
                         accH[j] = fma(bv[u][j], fs, accH[j]);
                         accQ[j] += bv[u][j];
@@ -513,8 +542,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     const int le = min(lane, nblk - 1);
                     const bool act = lane < nblk;
                     T av[8], bv[8];
-                    lds8(A_(r) + lb8, av);
-                    lds8(B_(r) + lb8, bv);
+                    lds8sw(A_(r) + lb8, sw, av);
+                    lds8sw(B_(r) + lb8, sw, bv);
                     const int ea = Ea_(r)[le], eb = Eb_(r)[le];
                     // alpha and beta mantissas are normalised separately (block maxima in [1,2)), so where one peaks the
                     // other can be ~2^-100: the products carry a constant 2^120 (2^960) so they stay normal numbers
@@ -536,16 +565,16 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     }
                     if (t >= 1) {
                         T pv[8];
-                        lds8(A_(r - 1) + lb8, pv);
+                        lds8sw(A_(r - 1) + lb8, sw, pv);
                         const int ep = Ea_(r - 1)[le];
                         // the left neighbour's last value, expressed in this block's exponent (bounded so den stays finite)
-                        T left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
+                        T left = __shfl_up_sync(ASG_FULL_MASK, last8(pv, fl), 1);
                         const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
                         left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep, Num<T>::kMaxShift - 8));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const T stay = hreg[j] * pv[j];
-                            const T den = fma(dreg[j], j ? pv[j ? j - 1 : 0] : left, stay);
+                            const T den = fma(dreg[j], prev8(pv, j, fl, left), stay);
                             // den == 0 implies a zero posterior, so the floor only guards 0/0
                             const T fs = fast_div(stay, tmax(den, Num<T>::tiny()));     // share of the mass that stayed (<= 1)
                             accH[j] = fma(bv[j], fs, accH[j]);
