@@ -36,6 +36,17 @@ namespace asg {
 constexpr int GRAD_MAX_CWARPS = 12;    // consumer warps (+ the producer's warpgroup)
 constexpr int GRAD_LBINS = 72;         // label bins per warp: L <= 64, bin L = trash (padding positions)
 
+// 64-bit add into shared memory as two native 32-bit atomics (a 64-bit shared atomicAdd compiles to a compare-and-swap
+// spin loop).  Exact: the thread whose add wraps the low word is the one -- and the only one -- that carries into the high
+// word, so the final 64-bit value is the modular sum in any order.  Readers must be separated by a barrier.
+__device__ __forceinline__ void add64_shared(unsigned long long *addr, unsigned long long v) {
+    unsigned *w = reinterpret_cast<unsigned *>(addr);
+    const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
+    const unsigned old = atomicAdd(w, vl);
+    const unsigned hi = vh + ((unsigned)(old + vl) < old ? 1u : 0u);
+    if (hi) atomicAdd(w + 1, hi);
+}
+
 // Fixed-point images (integers add in any order with the same result, so shared-memory atomics stay deterministic):
 //   posterior p of one position in one frame, 0 <= p <= 1, a frame sums to 1  -> p * kPost  (int32 / int64 bins)
 //   edge sums: posteriors (already in kPost units) summed over <= 2^24 frames -> 64-bit, kEdge units per unit mass
@@ -57,7 +68,7 @@ template <> struct Fix<double> {
     static constexpr double kInvPost = 1.0 / 4611686018427387904.0;
     __device__ __forceinline__ static unsigned long long to_fix(double q) { return (unsigned long long)__double2ll_rn(q); }
     __device__ __forceinline__ static double from_fix(unsigned long long q) { return (double)(long long)q; }
-    __device__ __forceinline__ static void add(unsigned long long *bin, unsigned long long q) { atomicAdd(bin, q); }
+    __device__ __forceinline__ static void add(unsigned long long *bin, unsigned long long q) { add64_shared(bin, q); }
     // 2^38 units per unit mass
     __device__ __forceinline__ static unsigned long long edge_fix(double acc) { return (unsigned long long)__double2ll_rn(acc * (1.0 / 16777216.0)); }
     __device__ __forceinline__ static double edge_unfix(unsigned long long q) { return (double)(long long)q * (1.0 / 274877906944.0); }
@@ -310,8 +321,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 for (int j = 0; j < 8; ++j) {
                     if (lab[j] < L) {
                         const int prevlab = prev8(lab, j, fl, labm1);
-                        atomicAdd(&gfix[lab[j] * L + lab[j]], FX::edge_fix(accH[j]));
-                        if (lane * 8 + (j ^ sw) >= 1) atomicAdd(&gfix[lab[j] * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
+                        add64_shared(&gfix[lab[j] * L + lab[j]], FX::edge_fix(accH[j]));
+                        if (lane * 8 + (j ^ sw) >= 1) add64_shared(&gfix[lab[j] * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
                     }
                     accH[j] = accQ[j] = T(0);
                 }
@@ -319,8 +330,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
         } else {
             for (int s = lane; s < Sn; s += 32) {
                 const int l = ylab[s];
-                atomicAdd(&gfix[l * L + l], FX::edge_fix(acc[s]));
-                if (s >= 1) atomicAdd(&gfix[l * L + ylab[s - 1]], FX::edge_fix(acc[sp + s] - acc[s]));
+                add64_shared(&gfix[l * L + l], FX::edge_fix(acc[s]));
+                if (s >= 1) add64_shared(&gfix[l * L + ylab[s - 1]], FX::edge_fix(acc[sp + s] - acc[s]));
                 acc[s] = T(0); acc[sp + s] = T(0);
             }
         }
