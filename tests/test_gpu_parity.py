@@ -437,10 +437,11 @@ def test_sharded_equals_whole(surf):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float64, TOL64)])
 @pytest.mark.parametrize("shape", [(1, 1, 1, 1), (2, 3, 1, 2), (7, 2, 8, 3), (9, 3, 9, 4), (12, 2, 64, 5), (11, 5, 65, 4),
-                                   (300, 2, 33, 257), (40, 3, 24, 40), (33, 1, 200, 9)])
+                                   (300, 2, 33, 257), (40, 3, 24, 40), (33, 1, 200, 9), (900, 1, 32, 800), (260, 2, 64, 200)])
 def test_shape_edges(surf, shape, dtype, tol):
     """Boundaries of the kernel families against the oracle: L = 1, L at the template steps (8/9), L = 64 | 65 (register-
-    resident E | large-alphabet path), S = 257 (two FAC consumer warps, the wide gradient path), S = T, N = 1."""
+    resident E | large-alphabet path), S = 257 (two FAC consumer warps, the wide gradient path), S = T, N = 1, S = 800 and
+    L = 64 (big frame records: the gradient kernel falls back to smaller tiles / fewer warps)."""
     T, N, L, S = shape
     r = np.random.default_rng(1000 + T + 7 * L + 13 * S)
     x = r.standard_normal((T, N, L))
