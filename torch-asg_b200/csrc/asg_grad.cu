@@ -90,6 +90,9 @@ template <> struct Pk<double> {
 // approximate (float) / exact (double) quotient for the edge posteriors
 __device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
+// correctly rounded reciprocal without the division's range checks (float), exact division (double)
+__device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
 
 // shared-memory map: [per-CTA block][stage 0][stage 1]...   A stage holds TB+1 frame records (the halo record of
 // frame t0-1 first) exactly as they lie in global memory, plus the tile's winv scalars.
@@ -460,12 +463,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 const T Z[2] = {z0, z1};
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const T invZ = (Z[u] > Num<T>::tiny()) ? T(1) / Z[u] : T(0);
-                    const T kq = wgt[u] * FX::kPost;
+                    // 1/Z and the lane's weight in one factor; the floor on Z keeps the factor finite (a frame whose total
+                    // product mass is below it has underflowed anyway: its posterior is dropped)
+                    const T c2 = (Z[u] > Num<T>::tiny() * FX::kPost * T(4)) ? rcp_(Z[u]) * (wgt[u] * FX::kPost) : T(0);
                     bin_t *bu = bins + u * GRAD_LBINS;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        bv[u][j] = (bv[u][j] * invZ) * kq;
+                        bv[u][j] = bv[u][j] * c2;
                         FX::add(&bu[lab[j]], FX::to_fix(bv[u][j]));
                     }
                 }
@@ -503,8 +507,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         z0 += __shfl_xor_sync(ASG_FULL_MASK, z0, o);
                         z1 += __shfl_xor_sync(ASG_FULL_MASK, z1, o);
                     }
-                    inv[0] = (z0 > T(0)) ? gf / z0 : T(0);
-                    inv[1] = (z1 > T(0)) ? gf / z1 : T(0);
+                    inv[0] = (z0 > T(0)) ? gf * rcp_(z0) : T(0);
+                    inv[1] = (z1 > T(0)) ? gf * rcp_(z1) : T(0);
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -567,11 +571,10 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     T wgt = T(0);
                     if (c != INT_MIN && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax);
                     const T Z = warp_sum(ps * wgt);
-                    const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
-                    const T kq = wgt * FX::kPost;
+                    const T c2 = (Z > Num<T>::tiny() * FX::kPost * T(4)) ? rcp_(Z) * (wgt * FX::kPost) : T(0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        bv[j] = (bv[j] * invZ) * kq;                   // posterior of position 8*lane+j, in fixed-point units
+                        bv[j] = bv[j] * c2;                            // posterior of position 8*lane+j, in fixed-point units
                         FX::add(&bins[lab[j]], FX::to_fix(bv[j]));
                     }
                     if (t >= 1) {
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 if (LP > 32 && lane + 32 < lpi) { al1 = Fa_(r)[lane + 32]; be1 = Fb_(r)[lane + 32]; }
                 g0 = al0 * be0; g1 = al1 * be1;
                 const T Z = warp_sum(g0 + g1);
-                const T inv = (Z > T(0)) ? gf / Z : T(0);
+                const T inv = (Z > T(0)) ? gf * rcp_(Z) : T(0);
                 g0 *= inv; g1 *= inv;
                 if (t >= 1) {                                  // no incoming edge at frame 0
                     const T winv = inv * Sc_(r);
