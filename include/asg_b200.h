@@ -193,6 +193,10 @@ int asg_profile_enable(int on);
 /* restrict the timing to the kernel ids whose bit is set (default: all).  Event pairs on the two scan streams cost
  * far more than the kernels' launch gaps, so a headline run times only the kernel whose roofline it reports. */
 int asg_profile_select(unsigned mask);
+/* time only every stride-th launch of each selected kernel (default 1 = every launch): an event pair around a kernel
+ * still costs the stream ~20 us of launch overlap, so a headline run samples the roofline kernel instead of timing
+ * every launch. */
+int asg_profile_stride(unsigned stride);
 int asg_profile_reset(void);
 int asg_profile_read(int kernel_id, double *total_ms, uint64_t *launches);
 const char *asg_kernel_name(int kernel_id);

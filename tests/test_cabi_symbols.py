@@ -33,7 +33,7 @@ def lib():
 def test_every_declared_symbol_is_exported(lib):
     names = declared_symbols()
     assert {"asg_layout", "asg_scan", "asg_grad", "asg_host_create", "asg_host_destroy", "asg_host_loss", "asg_host_submit", "asg_host_wait",
-            "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_select", "asg_profile_read"} <= set(names)
+            "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_select", "asg_profile_stride", "asg_profile_read"} <= set(names)
     for n in names:
         assert hasattr(lib, n), "libasg_b200.so does not export " + n
     assert b"sm_100a" in lib.asg_version()

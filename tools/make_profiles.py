@@ -49,7 +49,8 @@ L.append("bench.py (same build, not under a profiler, CUDA events on the launchi
 k = b["kernels"]
 for n, v in k.items():
     L.append("* `%s`: %.1f us average over %d launches%s" % (n, v["avg_us"], v["launches"],
-             " (separate pass: event pairs on the two scan streams would perturb the timed region)" if v.get("note") else " (inside the timed region)"))
+             " (separate pass: event pairs on the two scan streams would perturb the timed region)" if v.get("note") == "separate pass"
+             else " (%s)" % v.get("note", "inside the timed region")))
 live = sum(v["avg_us"] for v in k.values()); nt = sum(ncu_avg.values())
 L.append("")
 L.append("Shares of the four asg kernels, live vs ncu: " + ", ".join("%s %.1f%% vs %.1f%%" % (n.replace("_kernel", ""), 100 * k[n]["avg_us"] / live, 100 * ncu_avg[n] / nt) for n in k if n in ncu_avg) + ".")

@@ -23,6 +23,7 @@ struct ProfRec { cudaEvent_t a, b; int kid; };
 std::mutex g_prof_mu;
 std::atomic<int> g_prof_on{0};
 std::atomic<unsigned> g_prof_mask{0xffffffffu};
+std::atomic<unsigned> g_prof_stride{1};
 std::vector<ProfRec> g_prof_recs;       // recorded since the last read
 std::vector<ProfRec> g_prof_free;       // recycled event pairs
 double g_prof_ms[K_COUNT] = {0};
@@ -33,7 +34,10 @@ std::atomic<uint64_t> g_kid_launches[K_COUNT];
 LaunchScope::LaunchScope(int kid, cudaStream_t st) : kid_(kid), st_(st), slot_(-1) {
     count_launch();
     g_kid_launches[kid].fetch_add(1, std::memory_order_relaxed);
+    const uint64_t seq = g_kid_launches[kid].load(std::memory_order_relaxed);
     if (!g_prof_on.load(std::memory_order_relaxed) || !((g_prof_mask.load(std::memory_order_relaxed) >> kid) & 1u)) return;
+    const unsigned stride = g_prof_stride.load(std::memory_order_relaxed);
+    if (stride > 1 && (seq % stride) != 0) return;          // time every stride-th launch of a kernel only
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if ((int)g_prof_recs.size() >= PROF_SLOTS) return;
     ProfRec r;
@@ -365,6 +369,7 @@ int asg_profile_select(unsigned mask) {
     g_prof_mask.store(mask);
     return 0;
 }
+int asg_profile_stride(unsigned stride) { g_prof_stride.store(stride ? stride : 1, std::memory_order_relaxed); return ASG_OK; }
 int asg_profile_reset(void) {
     prof_drain();
     std::lock_guard<std::mutex> lk(g_prof_mu);
