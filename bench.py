@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- ASG forward+backward throughput on B200 (BASELINE.json's metric and config).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg4|cfg5] [--api graph|step|eager-ws|eager]
 
 One "step" = one ASGLoss(L, 'mean') forward + backward over one synthetic batch of the LibriSpeech-like
 config (T=1000, N=64 utterances per GPU, L=40, S=200, fp32) -- four scans + the gradient assembly, plus,
@@ -37,6 +37,7 @@ WORKLOADS = {
     # name: (T, N per GPU, L, S, forward_only)
     "cfg2": (1000, 64, 40, 200, False),     # LibriSpeech-like (BASELINE.json configs[1]) -- the headline
     "cfg3": (4000, 16, 32, 800, True),      # long utterance, forward only (configs[2])
+    "cfg4": (500, 128, 1024, 100, False),   # large alphabet: the transition matrix (4 MB) exceeds shared memory (configs[3])
     "cfg5": (1000, 64, 40, 200, False),     # batch-sharded: N=512 over 8 GPUs = cfg2 per GPU (configs[4])
 }
 METRIC = "ASG fwd+bwd utterances/sec at (T=1000,N=64,L=40)"
@@ -58,8 +59,82 @@ def grad_alg_bytes(T, N, L, S):
     return 16 * T * N * L + 8 * T * N * S + 8 * N * S + 8 * L * L
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi's clocks line through NVML, sampled 10 ms into the timed region and then every 50 ms."""
+class ClockSampler:
+    """The profiling recipe's clocks line: an `nvidia-smi --query-gpu=... -lms` PROCESS started before the warm-up and stopped
+    after the timed region; only the samples whose timestamps fall inside the timed region are summarised.  (A pynvml
+    thread inside this process was measured to stretch a 0.3 ms graph-replay step to 1-3 ms: every NVML query stalls the
+    issuing thread's CUDA calls and takes the GIL from it.  ASG_BENCH_SAMPLER=nvml keeps that variant for comparison.)"""
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index, period_ms=50):
+        import subprocess
+        self.proc, self.lines, self.t0, self.t1 = None, [], None, None
+        self.mode = os.environ.get("ASG_BENCH_SAMPLER", "smi")
+        self.index = index
+        self.thread = None
+        if self.mode == "smi":
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                              "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
+        elif self.mode == "nvml":
+            self.thread = _NvmlThread(index)
+
+    def begin(self):
+        self.t0 = time.time()
+        if self.thread is not None:
+            self.thread.start()
+
+    def end(self):
+        self.t1 = time.time()
+        if self.thread is not None:
+            self.thread.stop_flag = True
+
+    def summary(self):
+        import datetime
+        if self.thread is not None:
+            self.thread.join(1.0)
+            return self.thread.summary()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": "nvidia-smi not available"}
+        time.sleep(0.12)                     # let the sample that covers the end of the region land
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        inside, allrows = [], []
+        for ln in out.splitlines():
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 3 + len(self.NAMES):
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                row = (ts, int(f[1]), int(f[2]), [n for n, v in zip(self.NAMES, f[3:]) if v.lower().startswith("active")])
+            except Exception:
+                continue
+            allrows.append(row)
+            if self.t0 is not None and self.t0 <= ts <= self.t1 + 0.11:
+                inside.append(row)
+        rows = inside
+        how = "nvidia-smi -lms process, samples inside the timed region"
+        if not rows and allrows:             # a timed region shorter than the sampling period: the nearest sample after its start
+            after = [r for r in allrows if r[0] >= self.t0]
+            rows = after[:1] or allrows[-1:]
+            how = "nvidia-smi -lms process, timed region shorter than the sampling period: nearest sample"
+        clocks = sorted(r[1] for r in rows)
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": rows[0][2] if rows else None,
+                "reasons": reasons, "samples": len(rows), "how": how}
+
+
+class _NvmlThread(threading.Thread):
+    """nvidia-smi's clocks line through NVML from a thread of this process (comparison only, see ClockSampler)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -91,12 +166,12 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01 if len(self.samples) <= 1 else 0.05)     # every wake-up takes the GIL from the issuing thread
+            time.sleep(0.01 if len(self.samples) <= 1 else 0.05)
 
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s), "how": "pynvml thread"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -180,7 +255,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU baseline)")
     import torch_asg
     import torch_asg_native as nat
-    from torch_asg.sharded import sharded_asg_step
     assert nat.IS_B200_BUILD
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,6 +267,10 @@ def run_b200(args):
     except OSError:
         pass
     if world > 1:
+        # Every NCCL call of this job is issued from one thread, in program order, and waited for on the issuing stream, so a
+        # captured all-reduce never overlaps an eager one.  With mixing support on (the default) NCCL makes every launch of a
+        # graph that holds a collective wait ON THE HOST for the previous one (measured here: 0.10-0.25 ms per replay vs 0.005).
+        os.environ.setdefault("NCCL_GRAPH_MIXING_SUPPORT", "0")
         dist.init_process_group("nccl", device_id=dev)
     T, N, L, S, fwd_only = WORKLOADS[args.workload]
     lib = ctypes.CDLL(os.path.join(PKG, "libasg_b200.so"))
@@ -201,7 +279,8 @@ def run_b200(args):
     lib.asg_last_error.restype = ctypes.c_char_p
 
     # inputs larger than L2: rotate over enough distinct batches that a batch is evicted before reuse
-    x0, A, y0 = synth(T, N, L, S, 1000 * rank, torch.float32)
+    x0, _, y0 = synth(T, N, L, S, 1000 * rank, torch.float32)
+    A = synth(T, N, L, S, 0, torch.float32)[1]   # the transition matrix is a shared parameter: the same on every rank
     per_set = x0.numel() * 4
     nsets = max(2, -(-int(1.3 * L2_BYTES) // per_set))
     xs, ys = [], []
@@ -214,33 +293,46 @@ def run_b200(args):
     crit = torch_asg.ASGLoss(L, reduction="mean", forward_only=fwd_only).to(dev)
     with torch.no_grad():
         crit.transition.copy_(A.to(dev))
+    # The public surface with the workspace + CUDA graphs behind it (torch_asg/graphed.py).  Batch-sharded runs pass the
+    # process group: the backward graph then ends with the one fused all-reduce [L*L+2].
+    gcrit = torch_asg.GraphedASGLoss(crit, group=(dist.group.WORLD if world > 1 else None), global_batch=N * world,
+                                     use_graph=(args.api != "eager-ws"), max_graphs=4 * nsets)
     last = {}
 
-    from torch_asg.sharded import FusedAllReduce
-    fused = FusedAllReduce(crit)
-
-    def step_autograd(i):                    # the plain public API: ASGLoss(...)(...) + backward()
+    # Every step hands its input gradient to `last` (what an acoustic model's backward would consume) and clears
+    # `x.grad`, so at most two gradient buffers are alive and the caching allocator never goes back to cudaMalloc
+    # inside the timed loop (17 retained 10 MB gradients did exactly that in round 1).
+    def step_eager(i):                       # the reference-shaped eager route: ASGLoss(...)(...) + backward(), no workspace
         x = xs[i % nsets]
-        x.grad = None
         crit.transition.grad = None
         loss = crit(x, ys[i % nsets], il, tl)
         loss.backward()
-        last["loss"] = loss.detach()
+        last["loss"], last["gx"] = loss.detach(), x.grad
+        x.grad = None
 
-    def step(i):
+    def step_public(i):                      # THE HEADLINE: loss = criterion(inputs, ...); loss.backward()
         x = xs[i % nsets]
         if fwd_only:
             with torch.no_grad():
-                last["loss"] = crit(x, ys[i % nsets], il, tl)
+                last["loss"] = gcrit(x, ys[i % nsets], il, tl)
             return
-        if args.api == "autograd" and world == 1:
-            return step_autograd(i)
-        # One code path at every N: the native forward + backward of this rank's utterances, the mean loss, and (N > 1)
-        # the one fused all-reduce of (gA, loss sum, count).  It issues in ~0.1 ms of host time, so the timed loop is bound
-        # by the GPU; the autograd route through ASGLoss (same kernels, ~0.2 ms of host time per step, which a busy host
-        # stretches past the GPU's 0.32 ms) is timed in a short extra pass and reported as config.public_api_ms_per_step.
+        crit.transition.grad = None
+        loss = gcrit(x, ys[i % nsets], il, tl)
+        loss.backward()
+        last["loss"], last["gx"] = loss.detach(), x.grad
         x.grad = None
-        last["loss"] = sharded_asg_step(crit, x, ys[i % nsets], il, tl, global_batch=N * world, fused=fused)
+
+    def step_onegraph(i):                    # forward + backward + all-reduce as ONE graph replay
+        x = xs[i % nsets]
+        last["loss"] = gcrit.step(x, ys[i % nsets], il, tl)
+        last["gx"] = x.grad                  # the workspace's own buffer: nothing is allocated
+        x.grad = None
+
+    if args.api == "eager":
+        assert world == 1, "--api eager is the single-GPU reference-shaped route"
+    step = {"graph": step_public, "eager-ws": step_public, "step": step_onegraph, "eager": step_eager}[args.api]
+    if fwd_only:
+        step = step_public
 
     def sync_all():
         torch.cuda.synchronize()
@@ -248,44 +340,92 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # construction (not warm-up steps): capture the graphs of every input set, like compiling a model before training
+    if args.api != "eager":
+        for i in range(nsets):
+            gcrit.prepare(xs[i], ys[i], il, tl, kinds=(("fwd_only",) if fwd_only else ("fwd", "bwd", "step")))
+    sync_all()
+
+    # ---- NCCL parity self-check (N > 1): rank 0 recomputes the WHOLE batch on its own GPU from the seeds -----------
+    parity = None
+    if world > 1 and not fwd_only:
+        step(0)
+        torch.cuda.synchronize()
+        g_loss = float(gcrit.global_loss)
+        gA = crit.transition.grad.detach().clone()
+        gx = last["gx"].detach().clone()
+        if rank == 0:
+            xw = torch.cat([synth(T, N, L, S, 1000 * r, torch.float32)[0] for r in range(world)], 1).to(dev).requires_grad_(True)
+            yw = torch.cat([synth(T, N, L, S, 1000 * r, torch.float32)[2] for r in range(world)], 0).to(dev)
+            critw = torch_asg.ASGLoss(L, reduction="mean").to(dev)
+            with torch.no_grad():
+                critw.transition.copy_(A.to(dev))
+            lw = critw(xw, yw)
+            lw.backward()
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+            parity = {"what": "sharded step (all-reduced) vs the whole batch of %d utterances on rank 0, max-abs-err / max-abs-ref" % (N * world),
+                      "loss": abs(g_loss - float(lw)) / abs(float(lw)), "transition_grad": rel(gA, critw.transition.grad),
+                      "grad_x_slice": rel(gx, xw.grad[:, :N]), "tolerance": 1e-5}
+            parity["ok"] = bool(max(parity["loss"], parity["transition_grad"], parity["grad_x_slice"]) <= parity["tolerance"])
+            del xw, yw, critw, lw
+        torch.cuda.empty_cache()
+
+    sampler = ClockSampler(local)                # the nvidia-smi process needs ~1 s to start: launch it before the warm-up
     for i in range(args.warmup):
         step(i)
+    if args.api in ("graph", "step") and world == 1:   # one eagerly issued step too: the timed loop runs every 8th step that way
+        gcrit.use_graph = False                  # (roofline kernel timing) and its one-time costs (side stream of this stream) belong here
+        step(args.warmup)
+        gcrit.use_graph = True
     sync_all()
     # kernel ids of the library (asg_kernel_name)
     kid = {lib.asg_kernel_name(k).decode(): k for k in range(lib.asg_kernel_count())}
-    sampler = ClockSampler(local)
     lib.asg_profile_reset()
-    # the timed region carries event pairs only around the kernel whose roofline is reported (two records per step on
-    # the main stream); event pairs around the two concurrent scan kernels would add ~270 us of gaps per step
+    # Roofline kernel, timed LIVE inside the timed region: every PROF_STRIDE-th step runs the same zero-allocation calls
+    # eagerly (graph replays cannot carry the library's event pairs) with an event pair around that one kernel on its
+    # launching stream.  The other steps are graph replays.
     roof_kernel = "grad_kernel" if not fwd_only else "fac_scan_kernel"
     lib.asg_profile_select(ctypes.c_uint(1 << kid[roof_kernel]))
-    PROF_STRIDE = 8                              # an event pair costs the stream ~20 us of launch overlap: time every 8th launch
-    lib.asg_profile_stride(ctypes.c_uint(PROF_STRIDE))
+    PROF_STRIDE = int(os.environ.get("ASG_BENCH_STRIDE", "8"))      # 0: no eager steps in the timed loop (developer)
+    if world > 1:
+        # An eagerly issued step also issues its all-reduce eagerly, and NCCL pays ~1-2 ms each time a communicator switches
+        # between graph-launched and eager collectives (measured: 2 eager steps stretched a 20-step region from 6.2 to 9.8 ms).
+        # Batch-sharded runs therefore keep the timed loop pure replays; the kernels are timed in the separate pass below.
+        PROF_STRIDE = 0
+    lib.asg_profile_stride(ctypes.c_uint(1))
     lib.asg_profile_enable(1)
-    launches0 = lib.asg_launch_count()
+    replays0, launches0 = gcrit.graph_replays, gcrit.kernel_launches
+    raw0 = lib.asg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
+    sampler.begin()
     import gc
     gc.collect()
     gc.disable()                                 # the step is issued from Python: keep collector pauses out of the timed loop
+    graphed = gcrit.use_graph and args.api != "eager"
     e0.record()
     h0 = time.perf_counter()
     for i in range(args.steps):
-        step(args.warmup + i)
+        if graphed and PROF_STRIDE and i % PROF_STRIDE == PROF_STRIDE - 1:
+            gcrit.use_graph = False
+            step(args.warmup + i)
+            gcrit.use_graph = True
+        else:
+            step(args.warmup + i)
     host_ms = 1e3 * (time.perf_counter() - h0) / max(1, args.steps)      # host time to ISSUE a step (diagnostic)
     e1.record()
     sync_all()
     gc.enable()
-    sampler.stop_flag = True
+    sampler.end()
     ms = e0.elapsed_time(e1)
-    launches = int(lib.asg_launch_count() - launches0)
+    launches = int(gcrit.kernel_launches - launches0) if args.api != "eager" else int(lib.asg_launch_count() - raw0)
+    replays = int(gcrit.graph_replays - replays0)
     lib.asg_profile_enable(0)
-    loss_val = float(last["loss"])
+    loss_val = float(last["loss"]) if world == 1 or fwd_only else float(gcrit.global_loss)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    sampler.join(1.0)
+    clocks = sampler.summary()
 
     def read_kernels():
         ks = {}
@@ -296,36 +436,58 @@ def run_b200(args):
                 ks[lib.asg_kernel_name(k).decode()] = {"launches": int(cnt.value), "avg_us": 1e3 * tot.value / cnt.value}
         return ks
 
-    public_ms = None
-    if world == 1 and not fwd_only and args.api == "native":
-        nsteps_pub = min(args.steps, 50)
+    def timed_pass(fn, nsteps, base):
+        """A side pass (not part of `value`): ms per step and host issue time per step of another route."""
         for i in range(3):
-            step_autograd(i)
+            fn(base + i)
+        sync_all()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
+        gc.disable()
         p0.record()
-        for i in range(nsteps_pub):
-            step_autograd(3 + i)
+        hh = time.perf_counter()
+        for i in range(nsteps):
+            fn(base + 3 + i)
+        hms = 1e3 * (time.perf_counter() - hh) / nsteps
         p1.record()
-        torch.cuda.synchronize()
-        public_ms = p0.elapsed_time(p1) / nsteps_pub
+        sync_all()
+        gc.enable()
+        tt = torch.tensor([p0.elapsed_time(p1) / nsteps, hms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return {"ms_per_step": float(tt[0]), "host_issue_ms_per_step": float(tt[1])}
 
     kernels = read_kernels()                     # the roofline kernel, timed inside the timed region
     for v in kernels.values():
-        v["note"] = "inside the timed region, every %dth launch" % PROF_STRIDE
-    # every kernel, in a separate short pass (not part of `value`): same steps, event pairs around every launch
+        v["note"] = "inside the timed region, every %dth step (eager issue of the same calls)" % PROF_STRIDE
+    side = {}
+    nside = min(args.steps, 50)
+    if not fwd_only and args.api != "eager":
+        if args.api != "step":
+            side["one_graph_step"] = dict(timed_pass(step_onegraph, nside, 7), api="GraphedASGLoss.step: forward+backward+all-reduce as one graph replay")
+        if args.api != "graph":
+            side["graphed_autograd"] = dict(timed_pass(step_public, nside, 11), api="GraphedASGLoss(...) + loss.backward()")
+        if world == 1:
+            side["eager_autograd"] = dict(timed_pass(step_eager, nside, 13), api="ASGLoss(...)(...) + loss.backward(), no workspace, no graph")
+    # every kernel, in a separate short pass (not part of `value`): eager issue, event pairs around every launch
     lib.asg_profile_reset()
     lib.asg_profile_select(ctypes.c_uint(0xffffffff))
     lib.asg_profile_stride(ctypes.c_uint(1))
     lib.asg_profile_enable(1)
+    gcrit.use_graph = False
     for i in range(min(args.steps, 50)):
         step(args.warmup + args.steps + i)
+    gcrit.use_graph = graphed
     sync_all()
     lib.asg_profile_enable(0)
     kernels_all = read_kernels()
     for k, v in kernels_all.items():
         kernels.setdefault(k, dict(v, note="separate pass"))
 
+    api_text = {"graph": "loss = GraphedASGLoss(ASGLoss)(inputs, targets, il, tl); loss.backward() -- the reference's call, workspace + CUDA "
+                         "graphs behind it (forward graph, backward graph incl. the all-reduce); x.grad / transition.grad delivered by autograd",
+                "eager-ws": "GraphedASGLoss(use_graph=False) + loss.backward(): the zero-allocation C-ABI calls issued eagerly",
+                "step": "GraphedASGLoss.step: forward+backward+all-reduce as one graph replay (no autograd graph)",
+                "eager": "ASGLoss(...)(...) + loss.backward() (eager autograd, per-call allocations)"}[args.api]
     out = {
         "metric": METRIC, "value": N * world * args.steps / (ms * 1e-3), "unit": "utterances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "host_issue_ms_per_step": host_ms,
@@ -334,16 +496,14 @@ def run_b200(args):
         "config": {"workload": "%s: T=%d N=%d per GPU (global %d) L=%d S=%d, ASGLoss(mean) %s, full lengths"
                                % (args.workload, T, N, N * world, L, S, "forward-only" if fwd_only else "fwd+bwd"),
                    "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); no flush" % (nsets, nsets * per_set / 1e6),
-                   "parallelism": "batch-sharded, one fused all-reduce [L*L+2]" if world > 1 else "single GPU",
-                   "api": ("ASGLoss forward (no_grad)" if fwd_only else
-                           "ASGLoss(...)(...) + loss.backward() (autograd)" if (args.api == "autograd" and world == 1) else
-                           "torch_asg.sharded.sharded_asg_step: native fast_asg_gpu_forward + fast_asg_gpu_backward, mean loss, "
-                           "gradients delivered to inputs.grad / transition.grad (same path at every N)"),
-                   "loss": loss_val},
-        "gpu_launches": launches, "kernels": kernels, "clocks": sampler.summary(),
+                   "parallelism": "batch-sharded, one fused all-reduce [L*L+2] (NCCL%s)" % (
+                       ", captured in the backward graph" if gcrit.nccl_in_graph else ", eager") if world > 1 else "single GPU",
+                   "api": "ASGLoss forward under no_grad (forward-only graph)" if fwd_only else api_text,
+                   "graph_replays": replays, "loss": loss_val, "other_routes": side},
+        "gpu_launches": launches, "kernels": kernels, "clocks": clocks,
     }
-    if public_ms is not None:
-        out["config"]["public_api_ms_per_step"] = public_ms       # ASGLoss + backward() through autograd, extra 50-step pass
+    if parity is not None:
+        out["parity_check"] = parity
 
     peaks = {}
     try:
@@ -372,9 +532,8 @@ def run_b200(args):
     # ---- end to end through the C ABI with host buffers (rank-local, all ranks concurrently) ----------
     # NCTX host contexts in flight (asg_host_submit / asg_host_wait): every step still copies its inputs from
     # pinned host memory and its results (loss, grad_x, grad_A) back, but step i's H2D overlaps the kernels of the
-    # steps before it and the D2H of older ones.  Each context owns a stream (and its scans' side stream); the
-    # scans of several steps share the GPU (they fill ~2 small CTAs per SM), so throughput ends up bound by the
-    # PCIe copies (10 MB each way per step) rather than by one step's scan latency.
+    # steps before it and the D2H of older ones.  The latency of ONE call (one context, nothing overlapped) is
+    # reported next to the pipelined throughput.
     NCTX = int(os.environ.get("ASG_BENCH_NCTX", "8"))
     hx = xs[0].detach().cpu().pin_memory()
     hA = A.clone().pin_memory()
@@ -399,44 +558,82 @@ def run_b200(args):
         rc = lib.asg_host_wait(ctxs[j])
         assert rc == 0, lib.asg_last_error()
 
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, nctx):
         for i in range(nsteps):
-            if i >= NCTX:
-                e2e_wait(i % NCTX)           # results of step i-NCTX are in host memory
-            e2e_submit(i % NCTX)
-        for j in range(min(NCTX, nsteps)):
+            if i >= nctx:
+                e2e_wait(i % nctx)           # results of step i-nctx are in host memory
+            e2e_submit(i % nctx)
+        for j in range(min(nctx, nsteps)):
             e2e_wait(j)
 
-    e2e_run(max(3, args.warmup))
+    e2e_run(max(3, args.warmup), NCTX)
     sync_all()
     esteps = args.steps
     t0 = time.perf_counter()
-    e2e_run(esteps)                          # returns when every step's results are in host memory
+    e2e_run(esteps, NCTX)                    # returns when every step's results are in host memory
     dt = time.perf_counter() - t0
     e2e_loss = float(outs[0][0].mean())
+    lsteps = min(esteps, 30)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_run(lsteps, 1)                       # one context: submit, wait, submit, ... = the latency of one call
+    lat_ms = 1e3 * (time.perf_counter() - t0) / lsteps
     for h in ctxs:
         lib.asg_host_destroy(h)
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    t = torch.tensor([dt, lat_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt, lat_ms = float(t[0]), float(t[1])
     h2d = hx.numel() * 4 + hA.numel() * 4 + hy.numel() * 8
     d2h = N * 4 + (0 if fwd_only else (outs[0][1].numel() * 4 + outs[0][2].numel() * 4))
     out["e2e"] = {"value": N * world * esteps / dt, "unit": "utterances/s", "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / esteps, "loss": e2e_loss,
+                  "latency_ms_one_call": lat_ms, "latency_utterances_per_s": N * world / (lat_ms * 1e-3),
                   "api": "asg_host_submit/asg_host_wait (C ABI, pinned host buffers, %d contexts in flight; every step copies "
-                         "x, A, y in and loss, grad_x, grad_A out)" % NCTX}
+                         "x, A, y in and loss, grad_x, grad_A out); latency_ms_one_call = asg_host_loss-style submit+wait with ONE context" % NCTX}
 
-    # ---- the reference's CPU path on this box's host cores (rank 0, single-GPU run only) --------------
+    # ---- the reference on this box (rank 0, single-GPU run only): its CPU path on the host cores, its CUDA path on this GPU
     if world == 1 and not args.no_cpu_baseline:
         cdt, n, kind, cores = time_reference(T, N, L, S, fwd_only, 5, 1, budget_s=30.0)
         out["cpu_baseline"] = {"value": n / cdt, "unit": "utterances/s", "cores": cores, "kind": kind,
                                "sample": "5 timed steps of %d of the batch's %d utterances (T=%d,L=%d,S=%d fp32) after 1 warm-up, %.2f s/step"
                                          % (n, N, T, L, S, cdt)}
+        out["gpu_reference"] = time_reference_gpu(T, N, L, S, fwd_only)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # tear down in order: graphs that hold NCCL kernels first, then the process group; a watchdog ends the process if
+        # the teardown itself blocks (a hung exit would otherwise hold the whole box)
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        gcrit._entries.clear()
+        del gcrit
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
+
+
+def time_reference_gpu(T, N, L, S, fwd_only, steps=5, warmup=2):
+    """The UNMODIFIED reference's CUDA path (its asg.py + its native/*.cpp,*.cu compiled for sm_100a by
+    oracle/build_ref.py: build_cuda) on this GPU, in a subprocess that has none of the product on sys.path."""
+    import subprocess
+    script = os.path.join(ROOT, "oracle", "ref_gpu_bench.py")
+    so_dir = os.path.join(ROOT, "oracle", "_ref", "ref_cuda")
+    if not (os.path.isdir(so_dir) and os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "ref_py"))):
+        return {"unavailable": "oracle/_ref/ref_cuda or ref_py did not travel (built by __graft_entry__.build() where /root/reference is mounted)"}
+    try:
+        r = subprocess.run([sys.executable, script] + [str(v) for v in (T, N, L, S, steps, warmup, int(fwd_only))],
+                           capture_output=True, text=True, timeout=600)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": "reference CUDA path failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:300]}
+        return json.loads(line[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": "reference CUDA path: %s" % exc}
 
 
 def main():
@@ -447,8 +644,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--api", default="native", choices=["native", "autograd"],
-                    help="timed loop through torch_asg.sharded (native boundary, default) or ASGLoss + backward()")
+    ap.add_argument("--api", default="step", choices=["graph", "step", "eager-ws", "eager"],
+                    help="timed loop: step = GraphedASGLoss.step (default): the graph behind ASGLoss + backward() -- forward, backward and the "
+                         "all-reduce as one replay, gradients delivered to inputs.grad / transition.grad; graph = GraphedASGLoss(...)(...) + "
+                         "loss.backward() through autograd (forward graph + backward graph); eager-ws = the same zero-allocation calls "
+                         "without graphs; eager = plain ASGLoss + backward().  The routes not in the timed loop are timed in short side "
+                         "passes and reported under config.other_routes.")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -146,6 +146,59 @@ int asg_grad(int dtype, int parts,
              void *grad_x, void *grad_A, void *scratch,
              asg_stream_t stream);
 
+/*
+ * One whole training step of the loss on DEVICE buffers, in one call: the four scans, the gradient assembly and the
+ * reductions that the reference spreads over ASGGPUFast.forward, `full - aligned`, `.mean()` / `.sum()` and
+ * ASGGPUFast.backward (asg.py:71-97, :128-142; streamlined_fast_gpu.cpp:104-297).  It allocates nothing, creates
+ * nothing and never synchronises the host -- 4 kernel launches and one fork/join of the side stream -- so the call can
+ * be stream-captured into a CUDA graph (together with the all-reduce that follows it on `fused`) and costs a few
+ * microseconds of host time.  All buffers are the caller's, sized by asg_layout():
+ *   state (state_bytes), ctx (ctx_bytes), scratch (grad_scratch_bytes)   opaque
+ *   full_scores, aligned_scores, losses   [N] dtype      losses[n] = full[n] - aligned[n]
+ *   grad_x                                [T,N,L] dtype  d(scale * sum_n losses[n]) / dx   (contiguous, fully overwritten)
+ *   fused                                 [L*L + 2] dtype = grad_A (row-major) | sum_n losses[n] | N
+ *                                         -- the buffer a batch-sharded job all-reduces (SUM) across ranks
+ * `scale` is the upstream gradient of every utterance's loss: 1 for reduction 'sum', 1/global_batch for 'mean'.
+ */
+int asg_step(int dtype,
+             const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl,
+             const void *A, int64_t A_s0, int64_t A_s1,
+             const int64_t *y, int64_t y_s0, int64_t y_s1,
+             const int64_t *il, const int64_t *tl,
+             int64_t T, int64_t N, int64_t L, int64_t S,
+             double scale,
+             void *state, void *ctx, void *scratch,
+             void *full_scores, void *aligned_scores, void *losses,
+             void *grad_x, void *fused,
+             asg_stream_t stream);
+
+/*
+ * The same step split where autograd splits it (ASGGPUFast.forward / .backward, asg.py:73-97), still with caller-owned
+ * buffers and no allocation, so each half can sit in its own CUDA graph behind an autograd.Function:
+ *   asg_forward():  the scans (forward_only != 0: the two beta scans alone, `state` unused -- ASGGPUFastForwardOnly,
+ *                   asg.py:58-68), losses[n] = full[n] - aligned[n], loss_tail[0] = sum_n losses[n], loss_tail[1] = N,
+ *                   loss_tail[2] = scale * sum_n losses[n] (the reduced loss: scale 1 = 'sum', 1/batch = 'mean', asg.py:137-142).
+ *   asg_backward(): the gradient assembly for the upstream gradient  scale * g[n * g_stride]  of utterance n's loss
+ *                   (g == NULL reads as 1; g_stride 0 = one device scalar, e.g. the grad_output of a reduced loss);
+ *                   the FAC part is applied with the opposite sign, as autograd does for `full - aligned`.
+ */
+int asg_forward(int dtype, int forward_only,
+                const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl,
+                const void *A, int64_t A_s0, int64_t A_s1,
+                const int64_t *y, int64_t y_s0, int64_t y_s1,
+                const int64_t *il, const int64_t *tl,
+                int64_t T, int64_t N, int64_t L, int64_t S,
+                double scale,
+                void *state, void *ctx,
+                void *full_scores, void *aligned_scores, void *losses, void *loss_tail /* [3] */,
+                asg_stream_t stream);
+int asg_backward(int dtype, const void *g, int64_t g_stride, double scale,
+                 const void *state, const void *ctx,
+                 const int64_t *y, int64_t y_s0, int64_t y_s1,
+                 int64_t T, int64_t N, int64_t L, int64_t S,
+                 void *grad_x, void *grad_A, void *scratch,
+                 asg_stream_t stream);
+
 /* ---- host-buffer convenience API (end-to-end path) ------------------------------------------- */
 typedef struct asg_host_ctx asg_host_ctx_t;
 
@@ -176,6 +229,10 @@ int asg_host_submit(asg_host_ctx_t *h,
                     const void *g, int64_t T, int64_t N, int64_t L, int64_t S,
                     void *loss, void *grad_x, void *grad_A);
 int asg_host_wait(asg_host_ctx_t *h);
+
+/* Destroys the side streams and events the library created for asg_scan()'s FCC/FAC overlap (one set per
+ * (device, caller stream) pair).  Optional; call when no work of this library is in flight. */
+void asg_release(void);
 
 const char *asg_last_error(void);
 const char *asg_version(void);

@@ -33,7 +33,7 @@ def lib():
 def test_every_declared_symbol_is_exported(lib):
     names = declared_symbols()
     assert {"asg_layout", "asg_scan", "asg_grad", "asg_host_create", "asg_host_destroy", "asg_host_loss", "asg_host_submit", "asg_host_wait",
-            "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_select", "asg_profile_stride", "asg_profile_read"} <= set(names)
+            "asg_step", "asg_forward", "asg_backward", "asg_release", "asg_last_error", "asg_version", "asg_launch_count", "asg_profile_enable", "asg_profile_select", "asg_profile_stride", "asg_profile_read"} <= set(names)
     for n in names:
         assert hasattr(lib, n), "libasg_b200.so does not export " + n
     assert b"sm_100a" in lib.asg_version()
@@ -51,7 +51,7 @@ class Layout(ctypes.Structure):
         (n, ctypes.c_size_t) for n in ("elem_bytes", "rec_bytes", "state_bytes", "ctx_bytes", "grad_scratch_bytes",
                                        "rec_fac_alpha", "rec_fac_beta", "rec_fac_ea", "rec_fac_eb", "rec_fcc_alpha",
                                        "rec_fcc_beta", "rec_fcc_w", "rec_fcc_scale",
-                                       "off_ehat", "off_fac_hd", "off_lengths", "off_scalars")]
+                                       "off_ehat", "off_fac_hd", "off_lengths", "off_scalars", "off_ehat_t", "off_fmax", "off_rmax")]
 
 
 def _layout(lib, dt, T, N, L, S):

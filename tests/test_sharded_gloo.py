@@ -67,7 +67,7 @@ def _data():
     return x, y, il, tl, A
 
 
-def _worker(rank, world, port, reduction, q):
+def _worker(rank, world, port, reduction, q, explicit_batch=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -79,14 +79,22 @@ def _worker(rank, world, port, reduction, q):
         crit = TorchASG(A.shape[0], reduction)
         with torch.no_grad():
             crit.transition.copy_(A)
-        loss = sh.sharded_asg_step(crit, xs, ys, ils, tls, global_batch=x.shape[1])
+        # explicit_batch False: the global utterance count must come from an all-reduce (uneven shards: 3 + 2 utterances)
+        loss = sh.sharded_asg_step(crit, xs, ys, ils, tls, global_batch=x.shape[1] if explicit_batch else None)
         q.put((rank, float(loss), crit.transition.grad.numpy().copy(), xs.grad.numpy().copy(), crit.reduction))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("reduction", ["mean", "sum"])
-def test_two_rank_gloo_matches_single_process(reduction):
+def test_reduction_none_is_rejected():
+    sh = _sharded()
+    x, y, il, tl, A = _data()
+    with pytest.raises(ValueError):
+        sh.sharded_asg_step(TorchASG(A.shape[0], "none"), x.clone().requires_grad_(True), y, il, tl)
+
+
+@pytest.mark.parametrize("reduction,explicit_batch", [("mean", True), ("sum", True), ("mean", False)])
+def test_two_rank_gloo_matches_single_process(reduction, explicit_batch):
     sh = _sharded()
     x, y, il, tl, A = _data()
     crit = TorchASG(A.shape[0], reduction)
@@ -98,7 +106,7 @@ def test_two_rank_gloo_matches_single_process(reduction):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, reduction, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, reduction, q, explicit_batch)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])

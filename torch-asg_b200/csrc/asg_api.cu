@@ -115,13 +115,24 @@ static int scan_typed(int roles, const void *x, int64_t x_st, int64_t x_sn, int6
     return launch_scan<T>(a, roles, stream);
 }
 
+// what asg_step() adds to a gradient assembly: a uniform upstream gradient by value, and the loss / fused-tail outputs
+struct StepExtras {
+    double scale = 1.0;
+    const void *full = nullptr, *aligned = nullptr;
+    void *losses = nullptr, *tail = nullptr;
+};
+
 template <typename T>
 static int grad_typed(int parts, const void *g_full, int64_t gfs, const void *g_al, int64_t gas, const void *state,
                       const void *ctx, const int64_t *y, int64_t y_s0, int64_t y_s1, const asg_layout_t &lay, int64_t Tt,
-                      int64_t N, int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch, cudaStream_t stream) {
+                      int64_t N, int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch, cudaStream_t stream,
+                      const StepExtras *ex = nullptr) {
     GradArgs<T> a;
     a.g_full = (const T *)g_full; a.g_full_stride = gfs;
     a.g_aligned = (const T *)g_al; a.g_aligned_stride = gas;
+    a.gf_val = ex ? (T)ex->scale : T(1); a.ga_val = ex ? (T)(-ex->scale) : T(1);
+    a.full_scores = ex ? (const T *)ex->full : nullptr; a.aligned_scores = ex ? (const T *)ex->aligned : nullptr;
+    a.losses = ex ? (T *)ex->losses : nullptr; a.tail = ex ? (T *)ex->tail : nullptr;
     a.ctx = make_ctx<T>(const_cast<void *>(state), const_cast<void *>(ctx), lay, N);
     a.y = y; a.y_s0 = y_s0; a.y_s1 = y_s1;
     a.d = Dims{(int)Tt, (int)N, (int)L, (int)S};
@@ -150,6 +161,11 @@ template <typename T> __global__ void host_loss_kernel(const T *full, const T *a
 template <typename T> __global__ void host_g_kernel(const T *g, T *gpos, T *gneg, int N, int have_g) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) { T v = have_g ? g[n] : T(1); gpos[n] = v; gneg[n] = -v; }
+}
+
+template <typename T> __global__ void __launch_bounds__(256) losses_kernel(const T *full, const T *aligned, T *losses, int N, T *tail, T scale) {
+    __shared__ T red8[8];
+    write_losses_block<T>(full, aligned, losses, N, tail, red8, true, scale);
 }
 
 extern "C" {
@@ -242,6 +258,68 @@ int asg_grad(int dtype, int parts, const void *g_full, int64_t g_full_stride, co
     return cuda_fail(e, "asg_grad");
 }
 
+int asg_forward(int dtype, int forward_only, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0,
+                int64_t A_s1, const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl, int64_t T,
+                int64_t N, int64_t L, int64_t S, double scale, void *state, void *ctx, void *full_scores, void *aligned_scores,
+                void *losses, void *loss_tail, asg_stream_t stream) {
+    if (!full_scores || !aligned_scores || !losses || !loss_tail)
+        return fail(ASG_E_NULL, "asg_forward: full_scores, aligned_scores, losses and loss_tail are required");
+    int rc = asg_scan(dtype, forward_only ? ASG_ROLE_FORWARD_ONLY : ASG_ROLE_ALL, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1,
+                      il, tl, T, N, L, S, forward_only ? nullptr : state, ctx, full_scores, aligned_scores, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        LaunchScope ls(K_HOST_MISC, st);
+        if (dtype == ASG_F32) losses_kernel<float><<<1, 256, 0, st>>>((const float *)full_scores, (const float *)aligned_scores, (float *)losses, (int)N, (float *)loss_tail, (float)scale);
+        else losses_kernel<double><<<1, 256, 0, st>>>((const double *)full_scores, (const double *)aligned_scores, (double *)losses, (int)N, (double *)loss_tail, scale);
+    }
+    return cuda_fail((int)cudaGetLastError(), "asg_forward");
+}
+
+int asg_backward(int dtype, const void *g, int64_t g_stride, double scale, const void *state, const void *ctx, const int64_t *y,
+                 int64_t y_s0, int64_t y_s1, int64_t T, int64_t N, int64_t L, int64_t S, void *grad_x, void *grad_A, void *scratch,
+                 asg_stream_t stream) {
+    asg_layout_t lay;
+    int rc = asg_layout(dtype, T, N, L, S, &lay);
+    if (rc) return rc;
+    if (!state || !ctx || !y || !grad_x || !grad_A || !scratch) return fail(ASG_E_NULL, "asg_backward: state, ctx, y, grad_x, grad_A, scratch are required");
+    StepExtras ex;
+    ex.scale = scale;
+    int e;
+    if (dtype == ASG_F32)
+        e = grad_typed<float>(ASG_PART_BOTH, g, g_stride, g, g_stride, state, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch,
+                              (cudaStream_t)stream, &ex);
+    else
+        e = grad_typed<double>(ASG_PART_BOTH, g, g_stride, g, g_stride, state, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch,
+                               (cudaStream_t)stream, &ex);
+    return cuda_fail(e, "asg_backward");
+}
+
+int asg_step(int dtype, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0, int64_t A_s1,
+             const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl, int64_t T, int64_t N, int64_t L,
+             int64_t S, double scale, void *state, void *ctx, void *scratch, void *full_scores, void *aligned_scores,
+             void *losses, void *grad_x, void *fused, asg_stream_t stream) {
+    asg_layout_t lay;
+    int rc = asg_layout(dtype, T, N, L, S, &lay);
+    if (rc) return rc;
+    if (!x || !A || !y || !state || !ctx || !scratch || !full_scores || !aligned_scores || !losses || !grad_x || !fused)
+        return fail(ASG_E_NULL, "asg_step: every buffer is required (only il / tl may be NULL)");
+    rc = asg_scan(dtype, ASG_ROLE_ALL, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, T, N, L, S, state, ctx,
+                  full_scores, aligned_scores, stream);
+    if (rc) return rc;
+    StepExtras ex;
+    ex.scale = scale; ex.full = full_scores; ex.aligned = aligned_scores; ex.losses = losses;
+    ex.tail = (char *)fused + lay.elem_bytes * (size_t)L * L;
+    int e;
+    if (dtype == ASG_F32)
+        e = grad_typed<float>(ASG_PART_BOTH, nullptr, 0, nullptr, 0, state, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, fused, scratch,
+                              (cudaStream_t)stream, &ex);
+    else
+        e = grad_typed<double>(ASG_PART_BOTH, nullptr, 0, nullptr, 0, state, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, fused, scratch,
+                               (cudaStream_t)stream, &ex);
+    return cuda_fail(e, "asg_step");
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-buffer API
 // ---------------------------------------------------------------------------------------------
@@ -315,14 +393,20 @@ int asg_host_submit(asg_host_ctx_t *h, const void *x, const void *A, const int64
                       want_grad ? d + h->o_state : nullptr, d + h->o_ctx, d + h->o_full, d + h->o_al, st);
     if (rc) return rc;
     const int nb = (int)((N + 127) / 128);
-    if (h->dtype == ASG_F32) host_loss_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_full), (float *)(d + h->o_al), (float *)(d + h->o_loss), (int)N);
-    else host_loss_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_full), (double *)(d + h->o_al), (double *)(d + h->o_loss), (int)N);
-    { LaunchScope ls(K_HOST_MISC, st); }
+    {
+        LaunchScope ls(K_HOST_MISC, st);
+        if (h->dtype == ASG_F32) host_loss_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_full), (float *)(d + h->o_al), (float *)(d + h->o_loss), (int)N);
+        else host_loss_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_full), (double *)(d + h->o_al), (double *)(d + h->o_loss), (int)N);
+    }
+    ASG_TRY(cudaGetLastError(), "host_loss_kernel");
     ASG_TRY(cudaMemcpyAsync(loss, d + h->o_loss, eb * (size_t)N, cudaMemcpyDeviceToHost, st), "D2H loss");
     if (want_grad) {
-        if (h->dtype == ASG_F32) host_g_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_g), (float *)(d + h->o_g), (float *)(d + h->o_gneg), (int)N, g != nullptr);
-        else host_g_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_g), (double *)(d + h->o_g), (double *)(d + h->o_gneg), (int)N, g != nullptr);
-        { LaunchScope ls(K_HOST_MISC, st); }
+        {
+            LaunchScope ls(K_HOST_MISC, st);
+            if (h->dtype == ASG_F32) host_g_kernel<float><<<nb, 128, 0, st>>>((float *)(d + h->o_g), (float *)(d + h->o_g), (float *)(d + h->o_gneg), (int)N, g != nullptr);
+            else host_g_kernel<double><<<nb, 128, 0, st>>>((double *)(d + h->o_g), (double *)(d + h->o_g), (double *)(d + h->o_gneg), (int)N, g != nullptr);
+        }
+        ASG_TRY(cudaGetLastError(), "host_g_kernel");
         rc = asg_grad(h->dtype, ASG_PART_BOTH, d + h->o_g, 1, d + h->o_gneg, 1, d + h->o_state, d + h->o_ctx,
                       (const int64_t *)(d + h->o_y), S, 1, T, N, L, S, d + h->o_gx, d + h->o_gA, d + h->o_scr, st);
         if (rc) return rc;
@@ -347,6 +431,7 @@ int asg_host_loss(asg_host_ctx_t *h, const void *x, const void *A, const int64_t
     return asg_host_wait(h);
 }
 
+void asg_release(void) { release_side_slots(); }
 const char *asg_last_error(void) { return g_err; }
 const char *asg_version(void) { return "asg_b200 0.1 (sm_100a)"; }
 uint64_t asg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

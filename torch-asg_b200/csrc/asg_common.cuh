@@ -192,4 +192,30 @@ __device__ __forceinline__ void store8_stream(double *p, const double (&v)[8]) {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// One CTA of 256 threads: loss[n] = full[n] - aligned[n] (asg.py:128,136) and the fused tail of asg_step():
+// tail[0] = sum of the losses in a FIXED order (thread strides, shuffle tree, 8 partials: run-to-run deterministic),
+// tail[1] = the number of utterances, and (asg_forward only) tail[2] = scale * sum, the reduced loss.  An infeasible
+// utterance (aligned = -inf) makes the sum +inf, as the reference's own .sum() / .mean() does.
+template <typename T>
+__device__ __forceinline__ void write_losses_block(const T *full, const T *aligned, T *losses, int N, T *tail, T *red8,
+                                                   bool with_reduced = false, T scale = T(1)) {
+    T acc = T(0);
+    for (int n = threadIdx.x; n < N; n += 256) {
+        const T l = full[n] - aligned[n];
+        losses[n] = l;
+        acc += l;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T s = T(0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += red8[q];
+        tail[0] = s;
+        tail[1] = (T)N;
+        if (with_reduced) tail[2] = scale * s;
+    }
+}
+
 }  // namespace asg

@@ -236,8 +236,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     for (int i = 0; i < 8; ++i) { const int s = lane + 32 * i; if (s < sp) dst[s] = v[i]; }
                 }
                 if (role == 3 && lane == 0) {
-                    cscalT[buf * 2 + 0] = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
-                    cscalT[buf * 2 + 1] = FAC ? a.g_aligned[(int64_t)n * a.g_aligned_stride] : T(0);
+                    cscalT[buf * 2 + 0] = FCC ? a.gfull(n) : T(0);
+                    cscalT[buf * 2 + 1] = FAC ? a.galigned(n) : T(0);
                     cscalI[buf * 2 + 0] = (int)a.ctx.il[n];
                     cscalI[buf * 2 + 1] = Sn_;
                 }
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 ++useq;
             } else {
                 Tn = (int)a.ctx.il[n];
-                gf = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
-                ga = FAC ? a.g_aligned[(int64_t)n * a.g_aligned_stride] : T(0);
+                gf = FCC ? a.gfull(n) : T(0);
+                ga = FAC ? a.galigned(n) : T(0);
                 Sn = (int)a.ctx.tl[n];
                 const int64_t *yn = a.y + (int64_t)n * a.y_s0;
                 cbar();                        // the previous utterance's frames are done everywhere
@@ -742,9 +742,15 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 }
 
 // grad_A[e] = sum over CTAs of partial[c][e].  Fixed order: warp w sums parts w, w+8, ...; warp 0 adds the 8 sums.
+// With `losses` set (asg_step) one extra CTA also writes loss[n] = full[n] - aligned[n] and the fused tail (sum, count).
 template <typename T>
-__global__ void __launch_bounds__(256) grad_finalize_kernel(const T *partials, int nparts, int LL, T *grad_A) {
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const T *partials, int nparts, int LL, T *grad_A, const T *full,
+                                                            const T *aligned, T *losses, int N, T *tail) {
     __shared__ T red[8][33];
+    if (losses != nullptr && blockIdx.x == gridDim.x - 1) {
+        write_losses_block<T>(full, aligned, losses, N, tail, &red[0][0]);
+        return;
+    }
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
     T acc0 = T(0), acc1 = T(0);
@@ -818,7 +824,8 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     const int LL = L * L;
     {
         LaunchScope ls(K_GRAD_FINALIZE, st);
-        grad_finalize_kernel<T><<<(LL + 31) / 32, 256, 0, st>>>(a.partials, grid, LL, a.grad_A);
+        grad_finalize_kernel<T><<<(LL + 31) / 32 + (a.losses ? 1 : 0), 256, 0, st>>>(a.partials, grid, LL, a.grad_A, a.full_scores,
+                                                                                   a.aligned_scores, a.losses, a.d.N, a.tail);
     }
     return cudaGetLastError();
 }

@@ -77,8 +77,15 @@ template <typename T> struct ScanArgs {
 };
 
 template <typename T> struct GradArgs {
+    // upstream gradient of utterance n: gf_val * g_full[n * stride] (a NULL pointer reads as 1), likewise ga_val * g_aligned[..]
     const T *g_full; int64_t g_full_stride;
     const T *g_aligned; int64_t g_aligned_stride;
+    T gf_val, ga_val;
+    __device__ __forceinline__ T gfull(int64_t n) const { return g_full ? gf_val * g_full[n * g_full_stride] : gf_val; }
+    __device__ __forceinline__ T galigned(int64_t n) const { return g_aligned ? ga_val * g_aligned[n * g_aligned_stride] : ga_val; }
+    // asg_step(): the finalize kernel also writes loss[n] = full[n] - aligned[n] and the fused tail (sum, count)
+    const T *full_scores, *aligned_scores;
+    T *losses, *tail;
     Ctx<T> ctx;
     const int64_t *y; int64_t y_s0, y_s1;
     Dims d;
@@ -103,6 +110,7 @@ template <typename T> int launch_fcc_large(const ScanArgs<T> &a, int ndirs, cuda
 template <typename T> int launch_grad_large(const GradArgs<T> &a, int parts, cudaStream_t stream);
 int grad_grid_size(int device);   // number of persistent CTAs asg_grad launches
 void count_launch(int n = 1);
+void release_side_slots();          // asg_scan.cu: asg_release()
 
 // kernel ids for the launch counter / live profiler (asg_profile_* in include/asg_b200.h)
 enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_COUNT = 5 };

@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
     const int n = blockIdx.y;
     const int t_begin = blockIdx.x * GL_FRAMES;
     const int Tn = (int)a.ctx.il[n];
-    const T gf = FCC ? a.g_full[(int64_t)n * a.g_full_stride] : T(0);
-    const T ga = FAC ? a.g_aligned[(int64_t)n * a.g_aligned_stride] : T(0);
+    const T gf = FCC ? a.gfull(n) : T(0);
+    const T ga = FAC ? a.galigned(n) : T(0);
 
     // FAC constants of this lane's block (warp 0)
     T hreg[8], dreg[8], accH[8], accQ[8];
@@ -399,6 +399,11 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
 template <typename T, bool FCC, bool FAC>
 __global__ void grad_large_finish_kernel(const GradArgs<T> a, const T *G, const unsigned long long *edge) {
     const int L = a.d.L, N = a.d.N, sp = (int)a.ctx.sp;
+    if (a.losses != nullptr && blockIdx.x == gridDim.x - 1) {      // asg_step(): the extra CTA writes the losses and the fused tail
+        __shared__ T red8[8];
+        write_losses_block<T>(a.full_scores, a.aligned_scores, a.losses, N, a.tail, red8);
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L) return;
     T *out = a.grad_A + (int64_t)i * L;
@@ -407,7 +412,7 @@ __global__ void grad_large_finish_kernel(const GradArgs<T> a, const T *G, const 
         const double unfix = (sizeof(T) == 4) ? (1.0 / 4294967296.0) : (1.0 / 274877906944.0);
         for (int n = 0; n < N; ++n) {
             const int Sn = (int)a.ctx.tl[n];
-            const T ga = a.g_aligned[(int64_t)n * a.g_aligned_stride];
+            const T ga = a.galigned(n);
             const int64_t *yn = a.y + (int64_t)n * a.y_s0;
             int prev = -1;
             for (int s = 0; s < Sn; ++s) {
@@ -468,7 +473,7 @@ static int launch_grad_large_t(const GradArgs<T> &a, cudaStream_t st) {
     }
     {
         LaunchScope ls(K_GRAD_FINALIZE, st);
-        grad_large_finish_kernel<T, FCC, FAC><<<(L + 127) / 128, 128, 0, st>>>(a, G, edge);
+        grad_large_finish_kernel<T, FCC, FAC><<<(L + 255) / 256 + (a.losses ? 1 : 0), 256, 0, st>>>(a, G, edge);
     }
     return (int)cudaGetLastError();
 }

@@ -1118,9 +1118,24 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
 // stream and its fork/join events, so independent callers (several host contexts in flight, several host
 // threads) neither serialise on one shared side stream nor re-record each other's events.
 struct SideSlot { int device; cudaStream_t key, side; cudaEvent_t fork, join; };
+static std::mutex g_side_mu;
+static std::vector<SideSlot> g_side_slots;
+void release_side_slots() {
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const SideSlot &s : g_side_slots) {
+        cudaSetDevice(s.device);
+        cudaEventDestroy(s.fork);
+        cudaEventDestroy(s.join);
+        cudaStreamDestroy(s.side);
+    }
+    g_side_slots.clear();
+    cudaSetDevice(cur);
+}
 static bool side_slot(int device, cudaStream_t key, SideSlot &out) {
-    static std::mutex mu;
-    static std::vector<SideSlot> slots;
+    std::mutex &mu = g_side_mu;
+    std::vector<SideSlot> &slots = g_side_slots;
     std::lock_guard<std::mutex> lock(mu);
     for (const SideSlot &s : slots)
         if (s.device == device && s.key == key) { out = s; return true; }

@@ -33,9 +33,11 @@ void check_cuda(const Tensor &t, const char *what) {
                 "' must be a CUDA tensor -- this extension has no CPU implementation and no fallback");
 }
 
-// lengths / targets: int64 only, like the reference (utils.cpp:28,46; force_aligned_lattice.cpp:31-33)
-Tensor as_device_long(const Tensor &t, const Tensor &like, const char *what) {
+// lengths / targets: int64 only, like the reference (utils.cpp:28,46; force_aligned_lattice.cpp:31-33).
+// numel >= 0: the tensor must hold exactly that many elements (a short lengths / targets tensor would be read out of bounds)
+Tensor as_device_long(const Tensor &t, const Tensor &like, const char *what, int64_t numel = -1) {
     TORCH_CHECK(t.scalar_type() == at::kLong, "expected scalar type Long but found ", t.scalar_type(), " for ", what);
+    TORCH_CHECK(numel < 0 || t.numel() == numel, what, " must hold ", numel, " elements, got ", t.numel());
     Tensor r = t;
     if (r.device() != like.device()) r = r.to(like.device(), /*non_blocking=*/true);
     return r.contiguous();
@@ -86,7 +88,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> fully_connected_forward(Tensor &input
     check_inputs(inputs, transition, T, N, L);
     c10::cuda::CUDAGuard guard(inputs.device());
     const int dt = dtype_code(inputs, "inputs");
-    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths", N);
     const asg_layout_t lay = layout_of(dt, T, N, L, 1);
     auto opt = inputs.options().requires_grad(false);
     Tensor scores = at::empty({N}, opt);
@@ -126,9 +128,9 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> force_aligned_forward(Tensor &inputs,
     check_inputs(inputs, transition, T, N, L);
     c10::cuda::CUDAGuard guard(inputs.device());
     const int dt = dtype_code(inputs, "inputs");
-    Tensor y = as_device_long(targets, inputs, "targets");
-    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
-    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths");
+    Tensor y = as_device_long(targets, inputs, "targets", N * S);
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths", N);
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths", N);
     TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
@@ -154,7 +156,7 @@ std::tuple<Tensor, Tensor> force_aligned_backward(Tensor &grad_out, Tensor &alph
     TORCH_CHECK((size_t)path_contrib.numel() == lay.ctx_bytes && path_contrib.scalar_type() == at::kByte,
                 "path_contrib is not a context blob produced by this extension's force_aligned_forward");
     void *state = rec_base(alpha, lay, lay.rec_fac_alpha, "alpha");
-    Tensor y = as_device_long(targets, alpha, "targets");
+    Tensor y = as_device_long(targets, alpha, "targets", N * S);
     Tensor g = grad_out.to(alpha.options());
     auto opt = alpha.options().requires_grad(false);
     Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
@@ -171,9 +173,10 @@ Tensor fast_asg_gpu_forward_only(Tensor &inputs, Tensor &targets, Tensor &transi
     check_inputs(inputs, transition, T, N, L);
     c10::cuda::CUDAGuard guard(inputs.device());
     const int dt = dtype_code(inputs, "inputs");
-    Tensor y = as_device_long(targets, inputs, "targets");
-    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
-    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths");
+    Tensor y = as_device_long(targets, inputs, "targets", N * S);
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths", N);
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths", N);
+    TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
     Tensor full = at::empty({N}, opt), aligned = at::empty({N}, opt);
@@ -194,9 +197,9 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fast_asg_gpu_forward(
     check_inputs(inputs, transition, T, N, L);
     c10::cuda::CUDAGuard guard(inputs.device());
     const int dt = dtype_code(inputs, "inputs");
-    Tensor y = as_device_long(targets, inputs, "targets");
-    Tensor il = as_device_long(input_lengths, inputs, "input_lengths");
-    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths");
+    Tensor y = as_device_long(targets, inputs, "targets", N * S);
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths", N);
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths", N);
     TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
     const asg_layout_t lay = layout_of(dt, T, N, L, S);
     auto opt = inputs.options().requires_grad(false);
@@ -227,7 +230,7 @@ std::tuple<Tensor, Tensor> fast_asg_gpu_backward(Tensor &grad_full, Tensor &grad
     TORCH_CHECK(rec_base(full_gamma, lay, lay.rec_fcc_alpha, "full_gamma") == aligned_path_contrib.data_ptr() &&
                     rec_base(aligned_gamma, lay, lay.rec_fac_alpha, "aligned_gamma") == aligned_path_contrib.data_ptr(),
                 "saved tensors were not produced by the same fast_asg_gpu_forward call");
-    Tensor y = as_device_long(targets, full_gamma, "targets");
+    Tensor y = as_device_long(targets, full_gamma, "targets", N * S);
     Tensor gf = grad_full.to(full_gamma.options()), ga = grad_aligned.to(full_gamma.options());
     auto opt = full_gamma.options().requires_grad(false);
     Tensor grad_x = at::empty({T, N, L}, opt), grad_A = at::empty({L, L}, opt);
@@ -237,6 +240,74 @@ std::tuple<Tensor, Tensor> fast_asg_gpu_backward(Tensor &grad_full, Tensor &grad
                       T, N, L, S, grad_x.data_ptr(), grad_A.data_ptr(), scratch.data_ptr(), current_stream()));
     return {grad_A, grad_x};
 }
+
+// ------------------------------------------------------------------------------------------------
+// Workspace: every buffer one (dtype, T, N, L, S) problem needs, allocated ONCE, so a step is pure kernel launches
+// (asg_forward / asg_backward / asg_step allocate nothing and never synchronise) and can be captured in a CUDA graph.
+// torch owns the memory (the fused buffer is what torch.distributed all-reduces); the arithmetic is the C ABI's.
+struct Workspace {
+    int dt;
+    int64_t T, N, L, S;
+    asg_layout_t lay;
+    Tensor state, ctx, scratch, full, aligned, losses, loss_tail, grad_x, fused, gout;
+
+    Workspace(bool is_double, int64_t device, int64_t T_, int64_t N_, int64_t L_, int64_t S_) : T(T_), N(N_), L(L_), S(S_) {
+        dt = is_double ? ASG_F64 : ASG_F32;
+        lay = layout_of(dt, T, N, L, S);
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+        auto opt = at::TensorOptions().device(at::kCUDA, (c10::DeviceIndex)device).dtype(is_double ? at::kDouble : at::kFloat);
+        auto bopt = opt.dtype(at::kByte);
+        state = at::empty({(int64_t)lay.state_bytes}, bopt);
+        ctx = at::zeros({(int64_t)lay.ctx_bytes}, bopt);
+        scratch = at::empty({(int64_t)lay.grad_scratch_bytes}, bopt);
+        full = at::zeros({N}, opt);
+        aligned = at::zeros({N}, opt);
+        losses = at::zeros({N}, opt);
+        loss_tail = at::zeros({3}, opt);
+        grad_x = at::zeros({T, N, L}, opt);
+        fused = at::zeros({L * L + 2}, opt);
+        gout = at::ones({1}, opt);
+    }
+
+    void check(const Tensor &x, const Tensor &A, const Tensor &y, const Tensor &il, const Tensor &tl) const {
+        check_inputs(x, A, T, N, L);
+        TORCH_CHECK(dtype_code(x, "inputs") == dt, "inputs dtype differs from the workspace's");
+        TORCH_CHECK(x.device() == state.device(), "inputs are not on the workspace's device");
+        for (const Tensor *t : {&y, &il, &tl}) {
+            TORCH_CHECK(t->scalar_type() == at::kLong, "expected scalar type Long but found ", t->scalar_type());
+            TORCH_CHECK(t->device() == x.device(), "targets and lengths must be on the inputs' device (the workspace path never copies)");
+        }
+        TORCH_CHECK(y.dim() == 2 && y.size(0) == N && y.size(1) == S, "targets must be [N,S]");
+        TORCH_CHECK(il.dim() == 1 && il.size(0) == N && il.is_contiguous() && tl.dim() == 1 && tl.size(0) == N && tl.is_contiguous(),
+                    "lengths must be contiguous [N]");
+    }
+
+    void forward(Tensor &x, Tensor &A, Tensor &y, Tensor &il, Tensor &tl, bool forward_only, double scale) {
+        check(x, A, y, il, tl);
+        c10::cuda::CUDAGuard guard(x.device());
+        check_rc(asg_forward(dt, forward_only ? 1 : 0, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), A.data_ptr(), A.stride(0),
+                             A.stride(1), y.data_ptr<int64_t>(), y.stride(0), y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(),
+                             T, N, L, S, scale, state.data_ptr(), ctx.data_ptr(), full.data_ptr(), aligned.data_ptr(), losses.data_ptr(),
+                             loss_tail.data_ptr(), current_stream()));
+    }
+    // upstream gradient of utterance n's loss = scale * g[n] (g: [N]), or scale * g[0] for a one-element g
+    void backward(Tensor &g, double scale, Tensor &y) {
+        TORCH_CHECK(g.is_cuda() && g.device() == state.device() && dtype_code(g, "grad") == dt && (g.numel() == 1 || g.numel() == N),
+                    "grad must be a device tensor of 1 or N elements in the workspace's dtype");
+        c10::cuda::CUDAGuard guard(state.device());
+        check_rc(asg_backward(dt, g.data_ptr(), g.numel() == 1 ? 0 : (g.dim() ? g.stride(g.dim() - 1) : 0), scale, state.data_ptr(),
+                              ctx.data_ptr(), y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S, grad_x.data_ptr(),
+                              fused.data_ptr(), scratch.data_ptr(), current_stream()));
+    }
+    void step(Tensor &x, Tensor &A, Tensor &y, Tensor &il, Tensor &tl, double scale) {
+        check(x, A, y, il, tl);
+        c10::cuda::CUDAGuard guard(x.device());
+        check_rc(asg_step(dt, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), A.data_ptr(), A.stride(0), A.stride(1),
+                          y.data_ptr<int64_t>(), y.stride(0), y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(), T, N, L, S,
+                          scale, state.data_ptr(), ctx.data_ptr(), scratch.data_ptr(), full.data_ptr(), aligned.data_ptr(),
+                          losses.data_ptr(), grad_x.data_ptr(), fused.data_ptr(), current_stream()));
+    }
+};
 
 // ---- extras (not in the reference): introspection for tests and bench.py ------------------------
 Tensor ctx_scalars(Tensor &ctx, bool is_double, int64_t T, int64_t N, int64_t L, int64_t S) {
@@ -258,6 +329,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("fast_asg_gpu_forward_only", &fast_asg_gpu_forward_only, "fast ASG GPU forward only");
     m.def("fast_asg_gpu_forward", &fast_asg_gpu_forward, "fast ASG GPU forward");
     m.def("fast_asg_gpu_backward", &fast_asg_gpu_backward, "fast ASG GPU backward");
+    pybind11::class_<Workspace>(m, "Workspace",
+                                "persistent buffers of one (dtype, T, N, L, S) problem; forward/backward/step allocate nothing "
+                                "(CUDA-graph capturable).  Not in the reference: the host-independent step of this build.")
+        .def(pybind11::init<bool, int64_t, int64_t, int64_t, int64_t, int64_t>(), pybind11::arg("is_double"), pybind11::arg("device"),
+             pybind11::arg("T"), pybind11::arg("N"), pybind11::arg("L"), pybind11::arg("S"))
+        .def("forward", &Workspace::forward)
+        .def("backward", &Workspace::backward)
+        .def("step", &Workspace::step)
+        .def_readonly("full_scores", &Workspace::full)
+        .def_readonly("aligned_scores", &Workspace::aligned)
+        .def_readonly("losses", &Workspace::losses)
+        .def_readonly("loss_tail", &Workspace::loss_tail)
+        .def_readonly("grad_x", &Workspace::grad_x)
+        .def_readonly("fused", &Workspace::fused)
+        .def_readonly("gout", &Workspace::gout)
+        .def_readonly("state", &Workspace::state)
+        .def_readonly("ctx", &Workspace::ctx)
+        .def_readonly("T", &Workspace::T).def_readonly("N", &Workspace::N).def_readonly("L", &Workspace::L).def_readonly("S", &Workspace::S);
     m.def("_ctx_scalars", &ctx_scalars, "per-utterance float64 bookkeeping [N,8] of a context blob");
     m.def("_launch_count", []() { return asg_launch_count(); }, "kernels launched by libasg_b200 so far");
     m.def("_version", []() { return std::string(asg_version()); });

@@ -5,8 +5,14 @@ path (four scans + gradient assembly) on it, and the only cross-rank quantities 
 the transition gradient ``gA[L,L]`` (reference: the ``.sum({0,1})`` of ``fully_connected_lattice.cpp:60`` and
 the scatter of ``force_aligned_lattice.cpp:220-230`` both run over the batch) and the reduced loss
 (``asg.py:137-140``).  They travel in ONE all-reduce of a fused ``[L*L + 2]`` buffer
-(``gA``, ``sum of finite losses``, ``count of utterances``); ``grad_inputs`` never leaves its rank (it feeds
-that rank's acoustic model).  There is no other data-path collective.
+(``gA``, ``sum of the losses``, ``count of utterances``); ``grad_inputs`` never leaves its rank (it feeds
+that rank's acoustic model).  There is no other data-path collective.  Like the reference's own ``.sum()`` /
+``.mean()``, the loss sum is NOT filtered: one infeasible utterance (target longer than its input, loss ``+inf``)
+makes the reduced loss ``+inf`` on every rank (its gradients stay finite).
+
+This file is the EAGER sharded step (per-call allocations, a Python ``all_reduce``); the host-independent route --
+persistent workspace, CUDA graphs, the all-reduce captured in the backward graph -- is ``torch_asg.GraphedASGLoss``
+(``graphed.py``), which ``bench.py`` times.
 
 The reference itself has no distributed code; this is the B200-side answer to BASELINE.json's
 "Batch-sharded" config.  The arithmetic lives in the CUDA extension; this file is host plumbing only and
@@ -100,6 +106,18 @@ class FusedAllReduce:
         return self.loss_out, self.count_out
 
 
+def global_utterance_count(n_local, device, group=None):
+    """Sum of the ranks' local batch sizes.  Shards may be uneven (``shard_bounds`` gives the first ranks one extra), so
+    the count is all-reduced, never assumed to be ``n_local * world``: with 'mean' every rank must seed its backward
+    with the same ``1/global_batch``.  One small collective and a host read -- pass ``global_batch`` to skip it."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return n_local
+    t = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(round(float(t.item())))
+
+
 def _direct_step(criterion, native, inputs, targets, input_lengths, target_lengths, scale, fused):
     """Forward + backward of this rank's shard straight through the native boundary (no autograd graph): the two
     native calls, one loss sum and one copy of the transition gradient into the fused buffer.  The autograd engine
@@ -140,9 +158,12 @@ def sharded_asg_step(criterion, inputs, targets, input_lengths=None, target_leng
     """
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     n_local = inputs.shape[1]
-    if global_batch is None:
-        global_batch = n_local * world
     reduction = criterion.reduction
+    if reduction not in ('mean', 'sum'):
+        raise ValueError("sharded_asg_step reduces the loss over ALL ranks' utterances: reduction must be 'mean' or 'sum' "
+                         "(per-utterance losses never leave their rank -- call the criterion directly for reduction='none')")
+    if global_batch is None:
+        global_batch = global_utterance_count(n_local, inputs.device, group)
     if fused is None:
         fused = FusedAllReduce(criterion, group)
     scale = 1.0 / global_batch if reduction == 'mean' else 1.0
