@@ -141,6 +141,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// predicated store: no branch, no reconvergence point (a lone warp issues in order: a divergent `if` around a store costs a
+// BSSY/BSYNC pair and ~20 cycles of branch resolution)
+__device__ __forceinline__ void sts_f32_if(unsigned addr, float v, bool pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f32 [%0], %1;\n}\n" ::"r"(addr), "f"(v), "r"((unsigned)pred) : "memory");
+}
 __device__ __forceinline__ float4 lds_v4f32(unsigned addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

@@ -66,6 +66,100 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
         }
     };
     const int nb = (Tn + FB - 1) / FB;
+    // Fast path (contiguous, 16-byte aligned rows; L a multiple of 4): 16-byte copies, the row length walked in four
+    // predicated, unrolled vector steps, pointers advanced by one batch stride -- ~150 instructions per 8-frame batch
+    // instead of ~650 (measured: with the element-wise path the PRODUCER, not the recurrence, set the pace of both scan
+    // kernels at 176 ns per frame).
+    const bool vec = !gather && a.x_sl == 1 && (L & 3) == 0 && (a.x_st & 3) == 0 && (a.x_sn & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) && sizeof(T) == 4 && L <= 64 && (rp & 3) == 0 && (up & 3) == 0;
+    if (vec) {
+        const int V = L >> 2;                                   // 16-byte vectors per row
+        const int64_t bstep = (BETA ? -(int64_t)FB : (int64_t)FB) * a.x_st;
+        // this lane: frame f of a batch, vectors sub, sub+4, sub+8, sub+12
+        const T *src0 = xn + (int64_t)(BETA ? (Tn - 1 - f) : f) * a.x_st + 4 * sub;     // batch 0
+        const unsigned raw0 = smem_u32(raw) + (unsigned)sizeof(T) * (unsigned)(f * rp + 4 * sub);
+        const unsigned ur0 = smem_u32(uring) + (unsigned)sizeof(T) * (unsigned)(4 * sub);
+        auto issue_v = [&](int b) {
+            if (b * FB + f < Tn) {
+                const char *src = reinterpret_cast<const char *>(src0 + (int64_t)b * bstep);
+                const unsigned dst = raw0 + (unsigned)sizeof(T) * (unsigned)((b % NRAW) * FB * rp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (sub + 4 * i < V)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 64u * i), "l"(src + 64 * i) : "memory");
+            }
+        };
+        for (int b = 0; b < NRAW; ++b) {
+            if (b < nb) issue_v(b);
+            cp_async_commit();
+        }
+        double msum = 0.0;
+        int b = 0, g = 0;
+        while (b < nb || g < ngroups) {
+            const int c = consumed_min();
+            bool progressed = false;
+            if (g < ngroups && c >= min((g + 1) * FB, Tn)) {
+                flush(g);
+                ++g;
+                progressed = true;
+            }
+            const int hi = min((b + 1) * FB, Tn);
+            if (b < nb && hi - RING <= c) {
+                cp_async_wait<NRAW - 1>();
+                const int k = b * FB + f;
+                const bool valid = k < Tn;
+                const unsigned src = raw0 + (unsigned)sizeof(T) * (unsigned)((b % NRAW) * FB * rp);
+                float4 xv[4];
+                float m = Num<float>::neg_inf();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (valid && sub + 4 * i < V) {
+                        xv[i] = lds_v4f32(src + 64u * i);
+                        m = fmaxf(fmaxf(m, fmaxf(xv[i].x, xv[i].y)), fmaxf(xv[i].z, xv[i].w));
+                    }
+                }
+                m = fmaxf(m, __shfl_xor_sync(ASG_FULL_MASK, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(ASG_FULL_MASK, m, 2));
+                if (!(m > Num<float>::neg_inf())) m = 0.f;       // an all -inf frame
+                const unsigned dst = ur0 + (unsigned)sizeof(T) * (unsigned)((k % RING) * up);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (valid && sub + 4 * i < V) {
+                        float4 u;
+                        u.x = expf(xv[i].x - m); u.y = expf(xv[i].y - m); u.z = expf(xv[i].z - m); u.w = expf(xv[i].w - m);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 64u * i), "f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w) : "memory");
+                    }
+                }
+                if (valid && sub == 0) msum += (double)m;
+                if (b + NRAW < nb) issue_v(b + NRAW);
+                cp_async_commit();
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    st_volatile_s32(produced, hi);
+                }
+                ++b;
+                progressed = true;
+                if (b == nb) {
+                    cp_async_wait<0>();
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(ASG_FULL_MASK, msum, o);
+                    if (lane == 0) {
+                        *msum_out = msum;
+                        __threadfence_block();
+                        st_volatile_s32(msum_ready, 1);
+                    }
+                }
+            }
+            if (!progressed) __nanosleep(32);
+        }
+        if (nb == 0 && lane == 0) {
+            *msum_out = 0.0;
+            __threadfence_block();
+            st_volatile_s32(msum_ready, 1);
+        }
+        return;
+    }
     for (int b = 0; b < NRAW; ++b) {
         if (b < nb) issue(b);
         cp_async_commit();
@@ -357,35 +451,33 @@ __device__ __forceinline__ float2 lds_v2(unsigned addr) {
     return v;
 }
 
+// Work split of one step z = E p (LP x LP, LP a multiple of 8) over the 32 lanes of the lone consumer warp:
+//   lane = (g = lane / 4, q = lane % 4) owns the RG = LP/8 rows g*RG .. and the CQ = LP/4 columns q*CQ .. of E (in registers),
+// so a lane loads only ITS quarter of the feeding vector (2-5 vector LDS instead of the whole vector), runs RG independent
+// FFMA2 chains of CQ/2 links each (no long dependent chain: the issue rate, not the FMA latency, bounds the step), and the four
+// column-quarters of a row meet in two shuffle rounds.  Row r of a group is then finished (emission, scale, publish) by the
+// lane with q == r % 4.  Against the previous split (lane = one full row, the rows beyond 32 column-split): 25 FFMA2 + 7
+// loads + 10 shuffles per step instead of 25 FFMA2 + 19 loads + 4 shuffles in two serial halves.
 template <int LP, bool BETA>
 __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &sm, int n, int Tn, int lane) {
     typedef float T;
-    static_assert(LP >= 32, "the packed path covers LP >= 32");
-    constexpr int REM = LP - 32;                                  // rows handled with a column split
-    constexpr int RP = REM <= 8 ? 8 : (REM <= 16 ? 16 : 32);
-    constexpr int CH = 32 / RP;                                   // column chunks
-    constexpr int CL = LP / CH;                                   // columns per chunk (even)
+    static_assert(LP % 8 == 0 && LP >= 8 && LP <= 64, "LP is a multiple of 8 up to 64");
+    constexpr int RG = LP / 8, CQ = LP / 4, CQ2 = CQ / 2;
+    constexpr bool V4 = (CQ % 4) == 0;                            // the quarter is 16-byte aligned: LDS.128, else LDS.64
     const int L = a.d.L;
-    const int rr = lane % RP, cc = lane / RP;
-    const int row2 = 32 + rr;
-    const bool has2 = (REM > 0) && (rr < REM);
+    const int g = lane >> 2, q = lane & 3;
+    const int rbase = g * RG, cbase = q * CQ;
 
     const T R = transition_max(a.A, a.A_s0, a.A_s1, L, lane);
-    float2 E1[LP / 2];
-    float2 E2[REM > 0 ? CL / 2 : 1];
+    float2 E[RG][CQ2];
 #pragma unroll
-    for (int j = 0; j < LP / 2; ++j) {
-        E1[j].x = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, 2 * j, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, 2 * j, L, R);
-        E1[j].y = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, 2 * j + 1, lane, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, lane, 2 * j + 1, L, R);
-    }
-    if (REM > 0) {
+    for (int r = 0; r < RG; ++r)
 #pragma unroll
-        for (int c = 0; c < CL / 2; ++c) {
-            const int j = cc * CL + 2 * c;
-            E2[c].x = !has2 ? 0.f : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j, L, R));
-            E2[c].y = !has2 ? 0.f : (BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j + 1, row2, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, row2, j + 1, L, R));
+        for (int k = 0; k < CQ2; ++k) {
+            const int i = rbase + r, j = cbase + 2 * k;
+            E[r][k].x = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j, i, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, i, j, L, R);
+            E[r][k].y = BETA ? ehat_of(a.A, a.A_s0, a.A_s1, j + 1, i, L, R) : ehat_of(a.A, a.A_s0, a.A_s1, i, j + 1, L, R);
         }
-    }
     if (!BETA && n == 0) {   // publish E for the gradient assembly
         for (int e = lane; e < L * L; e += 32) a.ctx.ehat[e] = ehat_of(a.A, a.A_s0, a.A_s1, e / L, e % L, L, R);
     }
@@ -397,16 +489,17 @@ __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &s
     for (int l = lane; l < PR * LP; l += 32) { sm.pring[l] = T(0); if (BETA) sm.qring[l] = T(0); }
     __syncwarp();
 
-    // 32-bit shared addresses
+    // rows this lane finishes: rbase + q and (RG > 4) rbase + q + 4
+    const bool has0 = q < RG, has1 = q + 4 < RG;
+    const int row0 = rbase + q, row1 = rbase + q + 4;
     const unsigned pr0 = smem_u32(sm.pring), qr0 = smem_u32(sm.qring), sc0 = smem_u32(sm.scring), ur0 = smem_u32(sm.uring);
     constexpr unsigned ROWB = 4u * LP;
-    const unsigned l1 = 4u * (unsigned)lane, l2 = 4u * (unsigned)row2, ctail = 4u * (unsigned)(cc * CL);
-    const bool wlo = has2 && cc == 0;
+    const unsigned o0 = 4u * (unsigned)(has0 ? row0 : 0), o1 = 4u * (unsigned)(has1 ? row1 : 0), oc = 4u * (unsigned)cbase;
 
     int esum = 0;
     T sc = T(1);
     int e_next = 0;
-    T f1 = T(0), f2 = T(0);
+    T f0 = T(0), f1 = T(0);
 
     auto group_sync = [&](int k) {
         __threadfence_block();
@@ -418,77 +511,109 @@ __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &s
         while (ld_volatile_s32(&sm.flushed) < gneed) __nanosleep(20);
         __threadfence_block();
     };
-    auto publish = [&](int k, T v1, T v2, T w1, T w2, T applied) {
-        const unsigned slot = (unsigned)pslot<BETA>(k);
+    // feed = the vector the next step multiplies (alpha: the state, beta: u o state); st = the state (beta only).
+    // All stores are predicated (no divergent branch).  The maximum of the feeding vector goes through one REDUX whose
+    // result (Mred) is only READ in the next step, after that step's loads have been issued: a lone warp issues in order,
+    // so a result consumed right behind its producer would expose the full REDUX latency on every step.
+    T Mred = T(0);
+    const bool lane0 = lane == 0;
+    unsigned prev_off = 0;                  // byte offset (inside pring) of the row the previous step published
+    // One step.  uoff: byte offset of this frame's row in the u ring; slot: ring slot this frame's state goes to.
+    // In the main loop both are compile-time offsets from a per-group base (the loop is unrolled over the 8 frames of a
+    // group), so a step carries no address arithmetic, no loop counter and no group test.
+    auto step = [&](unsigned uoff, unsigned slot) {
+        const unsigned pin = pr0 + prev_off + oc;
+        float2 p[CQ2];
+        if (V4) {
+#pragma unroll
+            for (int i2 = 0; i2 < CQ / 4; ++i2) {
+                const float4 v = lds_v4(pin + 16u * i2);
+                p[2 * i2] = make_float2(v.x, v.y); p[2 * i2 + 1] = make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i2 = 0; i2 < CQ2; ++i2) p[i2] = lds_v2(pin + 8u * i2);
+        }
+        const T u0 = lds_f32(ur0 + uoff + o0);               // lanes without a row read row 0 of their group (weight 0 below)
+        const T u1 = (RG > 4) ? lds_f32(ur0 + uoff + o1) : T(0);
+        // this step's scale from the previous step's REDUX, behind the loads
+        pow2_fast(Mred, sc, e_next);
+        const T applied = sc;
+        esum += e_next;
+        float2 acc[RG];                                      // RG independent chains
+#pragma unroll
+        for (int r = 0; r < RG; ++r) acc[r] = __fmul2_rn(E[r][0], p[0]);
+#pragma unroll
+        for (int k2 = 1; k2 < CQ2; ++k2)
+#pragma unroll
+            for (int r = 0; r < RG; ++r) acc[r] = __ffma2_rn(E[r][k2], p[k2], acc[r]);
+        T zs[RG];
+#pragma unroll
+        for (int r = 0; r < RG; ++r) zs[r] = acc[r].x + acc[r].y;
+#pragma unroll
+        for (int r = 0; r < RG; ++r) zs[r] += __shfl_xor_sync(ASG_FULL_MASK, zs[r], 1);
+        const T ua0 = BETA ? applied : u0 * applied, ua1 = BETA ? applied : u1 * applied;
+#pragma unroll
+        for (int r = 0; r < RG; ++r) zs[r] += __shfl_xor_sync(ASG_FULL_MASK, zs[r], 2);
+        T z0 = zs[0], z1 = T(0);
+#pragma unroll
+        for (int r = 1; r < RG && r < 4; ++r) z0 = (q == r) ? zs[r] : z0;
+        if (RG > 4) {
+            z1 = zs[4];
+#pragma unroll
+            for (int r = 5; r < RG; ++r) z1 = (q == r - 4) ? zs[r] : z1;
+        }
+        T v0 = z0 * ua0, v1 = z1 * ua1;
+        if (!has0) v0 = T(0);
+        if (!(RG > 4 && has1)) v1 = T(0);
+        const T w0 = BETA ? v0 * u0 : v0, w1 = BETA ? v1 * u1 : v1;
+        f0 = w0; f1 = w1;
         const unsigned rowoff = slot * ROWB;
-        sts_f32(pr0 + rowoff + l1, BETA ? w1 : v1);
-        if (BETA) sts_f32(qr0 + rowoff + l1, v1);
-        if (wlo) { sts_f32(pr0 + rowoff + l2, BETA ? w2 : v2); if (BETA) sts_f32(qr0 + rowoff + l2, v2); }
-        if (!BETA && lane == 0) sts_f32(sc0 + 4u * slot, applied);
-        const T M = Num<T>::warp_max_nonneg(fmaxf(BETA ? w1 : v1, BETA ? w2 : v2));
-        pow2_fast(M, sc, e_next);
+        sts_f32_if(pr0 + rowoff + o0, w0, has0);
+        if (BETA) sts_f32_if(qr0 + rowoff + o0, v0, has0);
+        if (RG > 4) { sts_f32_if(pr0 + rowoff + o1, w1, has1); if (BETA) sts_f32_if(qr0 + rowoff + o1, v1, has1); }
+        if (!BETA) sts_f32_if(sc0 + 4u * slot, applied, lane0);
+        Mred = Num<T>::warp_max_nonneg(fmaxf(w0, w1));
+        prev_off = rowoff;
+        __syncwarp();
     };
 
     // ---- frame 0 --------------------------------------------------------------------------------
     group_sync(0);
     {
-        const T u1 = lds_f32(ur0 + l1);
-        const T u2 = has2 ? lds_f32(ur0 + l2) : T(0);
-        T v1, v2;
-        if (BETA) { v1 = (lane < L) ? T(1) : T(0); v2 = (has2 && row2 < L) ? T(1) : T(0); }
-        else { v1 = u1; v2 = u2; }
-        f1 = BETA ? v1 * u1 : v1; f2 = BETA ? v2 * u2 : v2;
-        publish(0, v1, v2, f1, f2, T(1));
+        const T u0 = has0 ? lds_f32(ur0 + o0) : T(0);
+        const T u1 = (RG > 4 && has1) ? lds_f32(ur0 + o1) : T(0);
+        T v0, v1;
+        if (BETA) { v0 = (has0 && row0 < L) ? T(1) : T(0); v1 = (has1 && row1 < L) ? T(1) : T(0); }
+        else { v0 = u0; v1 = u1; }
+        f0 = BETA ? v0 * u0 : v0; f1 = BETA ? v1 * u1 : v1;
+        const unsigned rowoff = (unsigned)pslot<BETA>(0) * ROWB;
+        sts_f32_if(pr0 + rowoff + o0, f0, has0);
+        if (BETA) sts_f32_if(qr0 + rowoff + o0, v0, has0);
+        if (RG > 4) { sts_f32_if(pr0 + rowoff + o1, f1, has1); if (BETA) sts_f32_if(qr0 + rowoff + o1, v1, has1); }
+        if (!BETA) sts_f32_if(sc0 + 4u * (unsigned)pslot<BETA>(0), T(1), lane0);
+        Mred = Num<T>::warp_max_nonneg(fmaxf(f0, f1));
+        prev_off = rowoff;
         __syncwarp();
     }
-    // ---- frames 1 .. Tn-1 -------------------------------------------------------------------------
-    for (int k = 1; k < Tn; ++k) {
-        if ((k & (FB - 1)) == 0) group_sync(k);
-        const unsigned urow = ur0 + (unsigned)(k & (RING - 1)) * ROWB;
-        const unsigned pin = pr0 + (unsigned)pslot<BETA>(k - 1) * ROWB;
-        // the whole feeding vector first: 10 broadcast LDS.128 (+ the tail chunk), then nothing but FFMA2
-        float4 q[LP / 4];
+    // ---- frames 1 .. Tn-1: the rest of group 0, whole groups (unrolled), the last partial group ------
+    int k = 1;
+    for (; k < min(FB, Tn); ++k) step((unsigned)(k & (RING - 1)) * ROWB, (unsigned)pslot<BETA>(k));
+    for (; k + FB <= Tn; k += FB) {
+        group_sync(k);
+        const unsigned ubase = (unsigned)(k & (RING - 1)) * ROWB, sbase = (unsigned)(k & (PR - 1));
 #pragma unroll
-        for (int i = 0; i < LP / 4; ++i) q[i] = lds_v4(pin + 16u * i);
-        float2 qt[REM > 0 ? CL / 2 : 1];
-        if (REM > 0) {
-#pragma unroll
-            for (int c = 0; c < CL / 2; ++c) qt[c] = lds_v2(pin + ctail + 8u * c);
-        }
-        const T u1 = lds_f32(urow + l1);
-        const T u2 = has2 ? lds_f32(urow + l2) : T(0);
-        const T applied = sc;
-        esum += e_next;
-        T z2 = T(0);
-        if (REM > 0) {
-            float2 t0 = make_float2(0.f, 0.f), t1 = t0;
-#pragma unroll
-            for (int c = 0; c < CL / 2; ++c) { if (c & 1) t1 = __ffma2_rn(E2[c], qt[c], t1); else t0 = __ffma2_rn(E2[c], qt[c], t0); }
-            t0 = __fadd2_rn(t0, t1);
-            z2 = t0.x + t0.y;
-#pragma unroll
-            for (int o = RP; o < 32; o <<= 1) z2 += __shfl_xor_sync(ASG_FULL_MASK, z2, o);
-        }
-        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-        for (int i = 0; i < LP / 4; ++i) {
-            if (i & 1) { a2 = __ffma2_rn(E1[2 * i], make_float2(q[i].x, q[i].y), a2); a3 = __ffma2_rn(E1[2 * i + 1], make_float2(q[i].z, q[i].w), a3); }
-            else { a0 = __ffma2_rn(E1[2 * i], make_float2(q[i].x, q[i].y), a0); a1 = __ffma2_rn(E1[2 * i + 1], make_float2(q[i].z, q[i].w), a1); }
-        }
-        a0 = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
-        const T z1 = a0.x + a0.y;
-        T v1, v2, w1, w2;
-        if (BETA) { v1 = z1 * applied; v2 = z2 * applied; w1 = v1 * u1; w2 = v2 * u2; }
-        else { v1 = z1 * (u1 * applied); v2 = z2 * (u2 * applied); w1 = v1; w2 = v2; }
-        f1 = w1; f2 = w2;
-        publish(k, v1, v2, w1, w2, applied);
-        __syncwarp();
+        for (int j = 0; j < FB; ++j) step(ubase + (unsigned)j * ROWB, sbase + (unsigned)(BETA ? FB - 1 - j : j));
+    }
+    if (k < Tn) {
+        group_sync(k);
+        for (; k < Tn; ++k) step((unsigned)(k & (RING - 1)) * ROWB, (unsigned)pslot<BETA>(k));
     }
     __threadfence_block();
     __syncwarp();
     if (lane == 0) st_volatile_s32(&sm.consumed, Tn);
 
-    T tot = warp_sum(f1 + (wlo ? f2 : T(0)));
+    T tot = warp_sum(f0 + f1);
     const double msum = wait_msum(&sm.msum, &sm.msum_ready);
     if (lane == 0) {
         const double score = (double)Num<T>::log_(tot) + msum + (double)(Tn - 1) * (double)R +
@@ -499,14 +624,13 @@ __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &s
     }
 }
 
-// dispatch: float with LP >= 32 -> packed specialisation, everything else -> generic
+// dispatch: float -> the tiled specialisation, double -> generic
 template <typename T, int LP, bool BETA> struct FccConsumer {
     __device__ static void run(const ScanArgs<T> &a, FccSmem<T, LP> &sm, int n, int Tn, int lane) { fcc_consumer<T, LP, BETA>(a, sm, n, Tn, lane); }
 };
 template <int LP, bool BETA> struct FccConsumer<float, LP, BETA> {
     __device__ static void run(const ScanArgs<float> &a, FccSmem<float, LP> &sm, int n, int Tn, int lane) {
-        if constexpr (LP >= 32) fcc_consumer_f32<LP, BETA>(a, sm, n, Tn, lane);
-        else fcc_consumer<float, LP, BETA>(a, sm, n, Tn, lane);
+        fcc_consumer_f32<LP, BETA>(a, sm, n, Tn, lane);
     }
 };
 
@@ -546,6 +670,7 @@ __global__ void __launch_bounds__(64, 1) fcc_scan_kernel(const ScanArgs<T> a) {
     const int dir = blockIdx.y == 0 ? a.dir0 : a.dir1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { sm.produced = 0; sm.consumed = 0; sm.msum_ready = 0; sm.flushed = 0; }
+    for (int l = threadIdx.x; l < RING * LP; l += blockDim.x) sm.uring[l] = T(0);   // the producer's vector path only writes l < L
     __syncthreads();
     int Tn = a.il ? (int)a.il[n] : a.d.T;
     Tn = max(0, min(Tn, a.d.T));
@@ -1023,6 +1148,7 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
 
     if (threadIdx.x == 0) { sm.flags[0] = 0; sm.flags[1] = 0; sm.flags[2] = 0; }
     if (threadIdx.x < W) sm.consumed[threadIdx.x] = 0;
+    for (int l = threadIdx.x; l < RING * up; l += nthreads) sm.uring[l] = T(0);     // incl. the always-zero slots of every row
     const int64_t *yn = a.y + (int64_t)n * a.y_s0;
     for (int s = threadIdx.x; s < sp; s += nthreads) {
         int lab = -1;
