@@ -20,11 +20,26 @@ template <> struct Num<float> {
     __device__ __forceinline__ static float log_(float v) { return logf(v); }
     __device__ __forceinline__ static float neg_inf() { return __int_as_float(0xff800000); }
     __device__ __forceinline__ static float tiny() { return 1.0e-37f; }
-    __device__ __forceinline__ static float prod_scale() { return 1.329227995784916e36f; }      // 2^120
+    static constexpr int kHalfProd = 55;       // alpha and beta mantissas each carry 2^55 (their normalised products 2^110)
+    __device__ __forceinline__ static float prod_scale() { return 1.2980742146337069e33f; }     // 2^110
     // 2^k for k in [-126,127] (clamped)
     __device__ __forceinline__ static float exp2i(int k) {
         k = max(-126, min(127, k));
         return __int_as_float((k + 127) << 23);
+    }
+    // Posterior weights of the gradient assembly.  A block's products alpha_j * beta_j * prod_scale live in units of
+    // 2^(ea + eb); pexp() is the biased exponent of the block's largest product, so ea + eb + pexp ranks the blocks of a
+    // frame by their TRUE largest product (the mantissas are not normalised to [1,2): the scans renormalise lazily, and
+    // inside a block alpha and beta can peak at opposite ends).  block_shift() is the power of two that brings a block to
+    // the units in which the frame's largest product is ~2^100; it can exceed the exponent range of a float factor (a
+    // dominant block may hold products as small as 2^-126), so it is APPLIED with ldexp_pos(), by exponent arithmetic.
+    __device__ __forceinline__ static int pexp(float pm) { return (__float_as_int(pm) >> 23) & 0xff; }
+    __device__ __forceinline__ static int block_shift(int c, int cmax_eff) { return max(c - cmax_eff, -100000) + (127 + 100); }
+    static constexpr int kPostLog2 = 30;
+    // v * 2^s for v >= 0 finite: flushed to zero when it underflows, saturated just below the overflow threshold
+    __device__ __forceinline__ static float ldexp_pos(float v, int s) {
+        const int b = __float_as_int(v), e = b >> 23, en = min(e + s, 253);
+        return (e <= 0 || en <= 0) ? 0.0f : __int_as_float((b & 0x007fffff) | (en << 23));
     }
     // For M >= 0: power-of-two `scale` with M*scale in [1,2) and e = -log2(scale).  M == 0, inf or
     // NaN leave the value alone.  A denormal M is only pulled up by 2^126 (the next frame finishes).
@@ -54,10 +69,18 @@ template <> struct Num<double> {
     __device__ __forceinline__ static double log_(double v) { return log(v); }
     __device__ __forceinline__ static double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
     __device__ __forceinline__ static double tiny() { return 1.0e-300; }
+    static constexpr int kHalfProd = 480;
     __device__ __forceinline__ static double prod_scale() { return 9.745314011399999e288; }     // 2^960
     __device__ __forceinline__ static double exp2i(int k) {
         k = max(-1022, min(1023, k));
         return __hiloint2double((k + 1023) << 20, 0);
+    }
+    __device__ __forceinline__ static int pexp(double pm) { return (__double2hiint(pm) >> 20) & 0x7ff; }
+    __device__ __forceinline__ static int block_shift(int c, int cmax_eff) { return max(c - cmax_eff, -100000) + (1023 + 900); }
+    static constexpr int kPostLog2 = 62;
+    __device__ __forceinline__ static double ldexp_pos(double v, int s) {
+        const int hi = __double2hiint(v), e = hi >> 20, en = min(e + s, 2045);
+        return (e <= 0 || en <= 0) ? 0.0 : __hiloint2double((hi & 0x000fffff) | (en << 20), __double2loint(v));
     }
     __device__ __forceinline__ static void pow2_norm(double M, double &scale, int &e) {
         int biased = (__double2hiint(M) >> 20) & 0x7ff;
@@ -83,6 +106,16 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
 template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
 template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+
+// ---------------------------------------------------------------------------------------------
+// Exponent word of one FAC block in a frame record: (E << 8) | (d + 8).  The block's eight stored mantissas m_j stand for
+// m_j * 2^(E + d); d = -floor(log2 max_j m_j), so m_j * 2^d has its block maximum in [1,2) and E is the exponent of that
+// normalised block.  The fp32 scans renormalise lazily (their stored mantissas drift inside [2^-40, 8)) and record the
+// drift d so that the gradient assembly still multiplies NORMALISED mantissas (full fp32 range for the in-block spread);
+// consumers that normalise on every frame store d = 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fac_pack(int E_raw, int d) { return ((E_raw - d) << 8) | ((d + 8) & 0xff); }
+__device__ __forceinline__ void fac_unpack(int w, int &E, int &d) { E = w >> 8; d = (w & 0xff) - 8; }
 
 // ---------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) -- element-granular so arbitrary (element-aligned) strides are accepted
@@ -145,6 +178,14 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
 // BSSY/BSYNC pair and ~20 cycles of branch resolution)
 __device__ __forceinline__ void sts_f32_if(unsigned addr, float v, bool pred) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.f32 [%0], %1;\n}\n" ::"r"(addr), "f"(v), "r"((unsigned)pred) : "memory");
+}
+// predicated streaming stores to global memory (no branch around them: see sts_f32_if)
+__device__ __forceinline__ void stg_cs_v4_if(void *p, float a, float b, float c, float d, bool pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %5, 0;\n@p st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n}\n"
+                 ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ void stg_s32_if(void *p, int v, bool pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.global.s32 [%0], %1;\n}\n" ::"l"(p), "r"(v), "r"((unsigned)pred) : "memory");
 }
 __device__ __forceinline__ float4 lds_v4f32(unsigned addr) {
     float4 v;

@@ -424,37 +424,41 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
             T bv[2][8];
             if (FAC) {
                 T av[2][8];
-                int ea[2], eb[2];
+                int ea[2], eb[2], da[2], db[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     lds8sw((const T *)(rowp[u] + offA), sw, av[u]);
                     lds8sw((const T *)(rowp[u] + offB), sw, bv[u]);
-                    ea[u] = *(const int *)(rowp[u] + offEa);
-                    eb[u] = *(const int *)(rowp[u] + offEb);
+                    fac_unpack(*(const int *)(rowp[u] + offEa), ea[u], da[u]);
+                    fac_unpack(*(const int *)(rowp[u] + offEb), eb[u], db[u]);
                 }
                 T pv[2][8];
-                int ep[2];
+                int ep[2];                                  // exponent of the RAW mantissas of frame t-1 (E + d)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     lds8sw((const T *)(rowp[u] - R + offA), sw, pv[u]);
-                    ep[u] = *(const int *)(rowp[u] - R + offEa);
+                    int e_, d_;
+                    fac_unpack(*(const int *)(rowp[u] - R + offEa), e_, d_);
+                    ep[u] = e_ + d_;
                 }
                 T ps[2];
-                int c[2];
+                int c[2], ce[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
+                    // normalised mantissas (block maximum in [1,2)), each carrying half of the product scale
+                    const T fa = Num<T>::exp2i(da[u] + Num<T>::kHalfProd), fb = Num<T>::exp2i(db[u] + Num<T>::kHalfProd);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bv[u][j] = av[u][j] * (bv[u][j] * Num<T>::prod_scale());
+                    for (int j = 0; j < 8; ++j) bv[u][j] = (av[u][j] * fa) * (bv[u][j] * fb);
                     const T pm = tmax(tmax(tmax(bv[u][0], bv[u][1]), tmax(bv[u][2], bv[u][3])), tmax(tmax(bv[u][4], bv[u][5]), tmax(bv[u][6], bv[u][7])));
                     ps[u] = ((bv[u][0] + bv[u][1]) + (bv[u][2] + bv[u][3])) + ((bv[u][4] + bv[u][5]) + (bv[u][6] + bv[u][7]));
-                    c[u] = (act && pm > T(0)) ? ea[u] + eb[u] : INT_MIN;
+                    c[u] = ea[u] + eb[u];
+                    ce[u] = (act && pm > T(0)) ? c[u] + Num<T>::pexp(pm) : INT_MIN;
                 }
-                const int cmax0 = __reduce_max_sync(ASG_FULL_MASK, c[0]);
-                const int cmax1 = __reduce_max_sync(ASG_FULL_MASK, c[1]);
-                T wgt[2];
-                wgt[0] = (c[0] != INT_MIN && c[0] - cmax0 >= -Num<T>::kMaxShift) ? Num<T>::exp2i(c[0] - cmax0) : T(0);
-                wgt[1] = (c[1] != INT_MIN && c[1] - cmax1 >= -Num<T>::kMaxShift) ? Num<T>::exp2i(c[1] - cmax1) : T(0);
-                T z0 = ps[0] * wgt[0], z1 = ps[1] * wgt[1];
+                const int cmax0 = __reduce_max_sync(ASG_FULL_MASK, ce[0]);
+                const int cmax1 = __reduce_max_sync(ASG_FULL_MASK, ce[1]);
+                const int sh[2] = {Num<T>::block_shift(c[0], cmax0), Num<T>::block_shift(c[1], cmax1)};
+                T z0 = (ce[0] != INT_MIN) ? Num<T>::ldexp_pos(ps[0], sh[0]) : T(0);
+                T z1 = (ce[1] != INT_MIN) ? Num<T>::ldexp_pos(ps[1], sh[1]) : T(0);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     z0 += __shfl_xor_sync(ASG_FULL_MASK, z0, o);
@@ -465,7 +469,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 for (int u = 0; u < 2; ++u) {
                     // 1/Z and the lane's weight in one factor; the floor on Z keeps the factor finite (a frame whose total
                     // product mass is below it has underflowed anyway: its posterior is dropped)
-                    const T c2 = (Z[u] > Num<T>::tiny() * FX::kPost * T(4)) ? rcp_(Z[u]) * (wgt[u] * FX::kPost) : T(0);
+                    const T c2 = (Z[u] > Num<T>::tiny() * FX::kPost * T(4) && ce[u] != INT_MIN)
+                                     ? Num<T>::ldexp_pos(rcp_(Z[u]), sh[u] + Num<T>::kPostLog2) : T(0);
                     bin_t *bu = bins + u * GRAD_LBINS;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -559,19 +564,22 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     T av[8], bv[8];
                     lds8sw(A_(r) + lb8, sw, av);
                     lds8sw(B_(r) + lb8, sw, bv);
-                    const int ea = Ea_(r)[le], eb = Eb_(r)[le];
-                    // alpha and beta mantissas are normalised separately (block maxima in [1,2)), so where one peaks the
-                    // other can be ~2^-100: the products carry a constant 2^120 (2^960) so they stay normal numbers
+                    int ea, eb, da, db;
+                    fac_unpack(Ea_(r)[le], ea, da);
+                    fac_unpack(Eb_(r)[le], eb, db);
+                    // alpha and beta mantissas are normalised separately (block maxima in [1,2) after the drift correction), so
+                    // where one peaks the other can be ~2^-100: the products carry a constant 2^110 (2^960) to stay normal numbers
+                    const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bv[j] = av[j] * (bv[j] * Num<T>::prod_scale());
+                    for (int j = 0; j < 8; ++j) bv[j] = (av[j] * fa) * (bv[j] * fb);
                     const T pm = tmax(tmax(tmax(bv[0], bv[1]), tmax(bv[2], bv[3])), tmax(tmax(bv[4], bv[5]), tmax(bv[6], bv[7])));
                     const T ps = ((bv[0] + bv[1]) + (bv[2] + bv[3])) + ((bv[4] + bv[5]) + (bv[6] + bv[7]));
-                    const int c = (act && pm > T(0)) ? ea + eb : INT_MIN;    // a block without mass is ignored
-                    const int cmax = __reduce_max_sync(ASG_FULL_MASK, c);
-                    T wgt = T(0);
-                    if (c != INT_MIN && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax);
-                    const T Z = warp_sum(ps * wgt);
-                    const T c2 = (Z > Num<T>::tiny() * FX::kPost * T(4)) ? rcp_(Z) * (wgt * FX::kPost) : T(0);
+                    const int c = ea + eb;
+                    const int ce = (act && pm > T(0)) ? c + Num<T>::pexp(pm) : INT_MIN;    // a block without mass is ignored
+                    const int cmax = __reduce_max_sync(ASG_FULL_MASK, ce);
+                    const int sh = Num<T>::block_shift(c, cmax);
+                    const T Z = warp_sum((ce != INT_MIN) ? Num<T>::ldexp_pos(ps, sh) : T(0));
+                    const T c2 = (Z > Num<T>::tiny() * FX::kPost * T(4) && ce != INT_MIN) ? Num<T>::ldexp_pos(rcp_(Z), sh + Num<T>::kPostLog2) : T(0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         bv[j] = bv[j] * c2;                            // posterior of position 8*lane+j, in fixed-point units
@@ -580,7 +588,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     if (t >= 1) {
                         T pv[8];
                         lds8sw(A_(r - 1) + lb8, sw, pv);
-                        const int ep = Ea_(r - 1)[le];
+                        int ep, dp_;
+                        fac_unpack(Ea_(r - 1)[le], ep, dp_);
+                        ep += dp_;                                 // exponent of the raw mantissas
                         // the left neighbour's last value, expressed in this block's exponent (bounded so den stays finite)
                         T left = __shfl_up_sync(ASG_FULL_MASK, last8(pv, fl), 1);
                         const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
@@ -603,9 +613,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         lds8(A_(r) + b * 8, av);
                         lds8(B_(r) + b * 8, bv);
                         T pm = T(0);
+                        int ea, eb, da, db;
+                        fac_unpack(Ea_(r)[b], ea, da);
+                        fac_unpack(Eb_(r)[b], eb, db);
+                        const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) pm = tmax(pm, av[j] * (bv[j] * Num<T>::prod_scale()));
-                        if (pm > T(0)) cmax = max(cmax, Ea_(r)[b] + Eb_(r)[b]);
+                        for (int j = 0; j < 8; ++j) pm = tmax(pm, (av[j] * fa) * (bv[j] * fb));
+                        if (pm > T(0)) cmax = max(cmax, ea + eb + Num<T>::pexp(pm));
                     }
                     cmax = __reduce_max_sync(ASG_FULL_MASK, cmax);
                     T zs = T(0);
@@ -613,11 +627,15 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         T av[8], bv[8];
                         lds8(A_(r) + b * 8, av);
                         lds8(B_(r) + b * 8, bv);
-                        const int c = Ea_(r)[b] + Eb_(r)[b];
+                        int ea, eb, da, db;
+                        fac_unpack(Ea_(r)[b], ea, da);
+                        fac_unpack(Eb_(r)[b], eb, db);
+                        const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
+                        const int c = ea + eb;
                         T pm = T(0), ps = T(0);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { const T p = av[j] * (bv[j] * Num<T>::prod_scale()); pm = tmax(pm, p); ps += p; }
-                        if (pm > T(0) && c - cmax >= -Num<T>::kMaxShift) zs += ps * Num<T>::exp2i(c - cmax);
+                        for (int j = 0; j < 8; ++j) { const T p = (av[j] * fa) * (bv[j] * fb); pm = tmax(pm, p); ps += p; }
+                        if (pm > T(0)) zs += Num<T>::ldexp_pos(ps, Num<T>::block_shift(c, cmax));
                     }
                     const T Z = warp_sum(zs);
                     const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
@@ -625,18 +643,27 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         T av[8], bv[8];
                         lds8(A_(r) + b * 8, av);
                         lds8(B_(r) + b * 8, bv);
-                        const int c = Ea_(r)[b] + Eb_(r)[b];
+                        int ea, eb, da, db;
+                        fac_unpack(Ea_(r)[b], ea, da);
+                        fac_unpack(Eb_(r)[b], eb, db);
+                        const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
+                        const int c = ea + eb;
                         T pm = T(0);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * (bv[j] * Num<T>::prod_scale())) * invZ; pm = tmax(pm, bv[j]); }
+                        for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * fa) * (bv[j] * fb); pm = tmax(pm, bv[j]); }
                         T wgt = T(0);
-                        if (pm > T(0) && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax) * FX::kPost;
+                        if (pm > T(0)) wgt = Num<T>::ldexp_pos(invZ, Num<T>::block_shift(c, cmax) + Num<T>::kPostLog2);
                         if (wgt == T(0)) continue;
                         T pv[8], left = T(0);
                         if (t >= 1) {
                             lds8(A_(r - 1) + b * 8, pv);
                             if (b > 0)
-                                left = A_(r - 1)[b * 8 - 1] * Num<T>::exp2i(min(Ea_(r - 1)[b - 1] - Ea_(r - 1)[b], Num<T>::kMaxShift - 8));
+                            {
+                                int e0, d0, e1, d1;
+                                fac_unpack(Ea_(r - 1)[b - 1], e0, d0);
+                                fac_unpack(Ea_(r - 1)[b], e1, d1);
+                                left = A_(r - 1)[b * 8 - 1] * Num<T>::exp2i(min((e0 + d0) - (e1 + d1), Num<T>::kMaxShift - 8));
+                            }
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {

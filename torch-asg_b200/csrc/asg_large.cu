@@ -320,20 +320,22 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
             const T *pa = a.ctx.fac_alpha(row) + b8, *pb = a.ctx.fac_beta(row) + b8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { av[j] = pa[j]; bv[j] = pb[j]; }
-            const int ea = a.ctx.fac_ea(row)[be], eb = a.ctx.fac_eb(row)[be];
+            int ea, eb, da, db;
+            fac_unpack(a.ctx.fac_ea(row)[be], ea, da);
+            fac_unpack(a.ctx.fac_eb(row)[be], eb, db);
+            const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
             T pm = T(0), ps = T(0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { bv[j] = av[j] * (bv[j] * Num<T>::prod_scale()); pm = tmax(pm, bv[j]); ps += bv[j]; }
-            const int c = (act && pm > T(0)) ? ea + eb : INT_MIN;
-            const int cmax = __reduce_max_sync(ASG_FULL_MASK, c);
-            T wgt = T(0);
-            if (c != INT_MIN && c - cmax >= -Num<T>::kMaxShift) wgt = Num<T>::exp2i(c - cmax);
-            const T Z = warp_sum(ps * wgt);
-            const T invZ = (Z > Num<T>::tiny()) ? T(1) / Z : T(0);
-            const T kq = wgt * FX::kPost;
+            for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * fa) * (bv[j] * fb); pm = tmax(pm, bv[j]); ps += bv[j]; }
+            const int c = ea + eb;
+            const int ce = (act && pm > T(0)) ? c + Num<T>::pexp(pm) : INT_MIN;
+            const int cmax = __reduce_max_sync(ASG_FULL_MASK, ce);
+            const int sh = Num<T>::block_shift(c, cmax);
+            const T Z = warp_sum((ce != INT_MIN) ? Num<T>::ldexp_pos(ps, sh) : T(0));
+            const T kq = (Z > Num<T>::tiny() && ce != INT_MIN) ? Num<T>::ldexp_pos(T(1) / Z, sh + Num<T>::kPostLog2) : T(0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                bv[j] = (bv[j] * invZ) * kq;
+                bv[j] = bv[j] * kq;
                 if (lab[j] >= 0) FX::add(&bins[lab[j]], FX::to_fix(bv[j]));
             }
             if (t >= 1) {
@@ -341,7 +343,9 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
                 const T *pp = a.ctx.fac_alpha(row - 1) + b8;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) pv[j] = pp[j];
-                const int ep = a.ctx.fac_ea(row - 1)[be];
+                int ep, dp_;
+                fac_unpack(a.ctx.fac_ea(row - 1)[be], ep, dp_);
+                ep += dp_;
                 T left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
                 const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
                 left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep, Num<T>::kMaxShift - 8));

@@ -840,7 +840,7 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
         // store mantissas + exponent
         if (store) {
             store8_stream(stp, v);
-            if (store_e) *esp = Eme;
+            if (store_e) *esp = fac_pack(Eme, 0);
         }
         stp += sstep;
         esp += estep;
@@ -909,7 +909,6 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
     const int64_t sstep = (BETA ? -a.ctx.R : a.ctx.R) / (int64_t)sizeof(T);
     const int64_t estep = (BETA ? -a.ctx.R : a.ctx.R) / (int64_t)sizeof(int);
     const bool store_e = store && lane < nblk;
-    const float edge_mask = BETA ? (lane == 31 ? 0.f : 1.f) : (lane == 0 ? 0.f : 1.f);
 
     // pairs: index q holds positions (q, q+4) of this lane's block
     float2 h2[4], d2[4];
@@ -927,23 +926,72 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
 
     float2 P[4];         // alpha: state = feed; beta: state Q
     float2 Wf[4];        // beta: feed = Q o u
-    int Eme = 0;
-    float mymax = 0.f;
-    float nv = 0.f;      // neighbour's boundary value of the previous step, expressed in 2^ne
+    int Eme = 0;         // the block's exponent: the mantissas below are in units of 2^Eme
+    float nv = 0.f;      // neighbour's boundary value of the previous step, in units of 2^ne
     int ne = 0;
+    bool fix = false;    // some block of the warp needs the slow path (renormalise / adopt / pull up) before its next step
 #pragma unroll
     for (int q = 0; q < 4; ++q) { P[q] = make_float2(0.f, 0.f); Wf[q] = P[q]; }
 
-    unsigned slot_off = 0;                            // byte offset of ring slot (k % RING)
-    for (int k = 0; k < Tn; ++k) {
-        const int t = BETA ? (Tn - 1 - k) : k;
-        if ((k & (FB - 1)) == 0) {
-            if (lane == 0) st_volatile_s32(&sm.consumed[0], k);
-            const int need = min(k + FB, Tn);
-            while (ld_volatile_s32(&sm.flags[vec ? 2 : 0]) < need) __nanosleep(20);
-            __threadfence_block();
+    // LAZY block floating point.  A step is only the recurrence itself -- 12 packed multiply-adds on the block's eight
+    // mantissas plus the neighbour's boundary value, which arrives already expressed in this block's units (`nva`; flushed
+    // to zero when it is more than 2^126 below: real mass is never clamped), one shuffle of (boundary value, exponent)
+    // -- and a range check.  The expensive part (maximum -> power of two -> rescale -> exponent update; re-basing the
+    // block on the exponent of what flows in when mass first reaches an empty block or when the inflow would exceed the
+    // mantissa range) runs only when some block of the warp asks for it: the block maximum has drifted outside [2^-40, 4),
+    // or the inflow is >= 4 in the block's units.  That is a warp-uniform branch taken every few frames instead of ~60
+    // instructions on every frame.  Boundary values always travel WITH the exponent they are expressed in, so blocks
+    // renormalise independently of each other.  Stored mantissas stay below 2^3 (a block is renormalised as soon as its
+    // maximum passes 4 and can at most double before that happens; inflow >= 4 is re-based before it is used): the
+    // gradient assembly multiplies alpha and beta mantissas with a constant 2^110.
+    float nva = 0.f;     // the neighbour's boundary value of the previous step in THIS block's units (2^Eme)
+    auto to_mine = [&]() {                                         // nv * 2^(ne - Eme), flushed below 2^-126
+        const int dl = min(max(ne - Eme, -127), 127);
+        return nv * __int_as_float((dl + 127) << 23);
+    };
+    auto fix_block = [&]() {
+        const float m = max8(P);
+        if (m > 0.f) {
+            float sc; int e;
+            Num<T>::pow2_norm(m, sc, e);
+            const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { P[q] = __fmul2_rn(P[q], sc2); if (BETA) Wf[q] = __fmul2_rn(Wf[q], sc2); }
+            Eme += e;
         }
-        float2 u2[4];
+        nva = to_mine();
+        if (nv > 0.f && (!(m > 0.f) || !(nva < 4.f))) {
+            // re-base on the inflow: afterwards it is in [1,2) and this block's own mantissas have shrunk accordingly
+            float sn; int en;
+            Num<T>::pow2_norm(nv, sn, en);
+            const int En = ne + en;
+            const int sh = min(max(Eme - En, -127), 0);
+            const float f = __int_as_float((sh + 127) << 23);
+            const float2 f2 = make_float2(f, f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { P[q] = __fmul2_rn(P[q], f2); if (BETA) Wf[q] = __fmul2_rn(Wf[q], f2); }
+            Eme = En;
+            nva = nv * sn;
+        } else if (!(m > 0.f)) {
+            Eme = ne;                                               // empty and nothing flows in: follow the neighbour
+            nva = 0.f;
+        }
+    };
+
+    unsigned slot_off = 0;                            // byte offset of ring slot (k % RING)
+    char *sptr = reinterpret_cast<char *>(stp), *eptr = reinterpret_cast<char *>(esp);
+    const int64_t rstep = BETA ? -a.ctx.R : a.ctx.R;
+    const bool lane0 = lane == 0;
+    const bool real = lane < nblk;                    // lanes beyond the last block hold zeros and never ask for the slow path
+    const bool edge = BETA ? lane == 31 : lane == 0;
+
+    auto ring_sync = [&](int k) {                     // frames < k are done with; frames k .. k+FB-1 must be in the ring
+        if (lane0) st_volatile_s32(&sm.consumed[0], k);
+        const int need = min(k + FB, Tn);
+        while (ld_volatile_s32(&sm.flags[vec ? 2 : 0]) < need) __nanosleep(20);
+        __threadfence_block();
+    };
+    auto load_u = [&](float2 (&u2)[4]) {
         if (vec) {
             const float4 ua = lds_v4f32(pa + slot_off), ub = lds_v4f32(pa + slot_off + 16u);
             u2[0] = make_float2(ua.x, ua.y); u2[1] = make_float2(ua.z, ua.w);
@@ -952,87 +1000,91 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
 #pragma unroll
             for (int q = 0; q < 4; ++q) { u2[q].x = lds_f32(la[q] + slot_off); u2[q].y = lds_f32(la[q + 4] + slot_off); }
         }
-        slot_off = ((k & (RING - 1)) == RING - 1) ? 0u : slot_off + slot_bytes;
+    };
+    // exchange, range check, stores: the common tail of every step.  No lane-divergent branch anywhere in a step (the
+    // stores are predicated), so the warp-wide shuffles and the vote need no convergence barriers.
+    auto finish = [&](float snd) {
+        // hand the boundary to the neighbour together with the exponent it is expressed in
+        nv = BETA ? __shfl_down_sync(ASG_FULL_MASK, snd, 1) : __shfl_up_sync(ASG_FULL_MASK, snd, 1);
+        ne = BETA ? __shfl_down_sync(ASG_FULL_MASK, Eme, 1) : __shfl_up_sync(ASG_FULL_MASK, Eme, 1);
+        nv = edge ? 0.f : nv;                                      // an edge lane gets its own value back: no neighbour
+        nva = to_mine();
+        const float m = max8(P);
+        const unsigned me = (unsigned)__float_as_int(m) >> 23;     // m >= 0
+        // block maximum out of [2^-40, 4) (also inf/NaN) | mass reaching an empty block | inflow beyond the mantissa range
+        const bool live = me != 0u;
+        const bool flag = real & ((live & ((me - 87u) > 41u)) | ((nv > 0.f) & ((!live) | !(nva < 4.f))));
+        fix = __any_sync(ASG_FULL_MASK, flag);
+        stg_cs_v4_if(sptr, P[0].x, P[1].x, P[2].x, P[3].x, store);
+        stg_cs_v4_if(sptr + 16, P[0].y, P[1].y, P[2].y, P[3].y, store);
+        stg_s32_if(eptr, fac_pack(Eme, live ? 127 - (int)me : 0), store_e);     // E and the drift of the block maximum
+        sptr += rstep;
+        eptr += rstep;
+    };
+    // No band masks here: a position that cannot be reached from the start (s > t) never receives mass, and one that can
+    // no longer reach the end has beta = 0 exactly, so its alpha never enters a posterior (the generic consumer zeroes both).
+    auto step = [&]() {
+        float2 u2[4];
+        load_u(u2);
+        if (fix) fix_block();                                  // warp-uniform
+        float2 r2[4];
+        float snd;
+        if (BETA) {
+            // r[j] = h[j] w[j] + d[j] w[j+1];  pair (j, j+4) needs (w[j+1], w[j+5]) = pair j+1; j = 3: (w[4], inflow)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 nx = (q < 3) ? Wf[(q + 1) & 3] : make_float2(Wf[0].y, nva);
+                r2[q] = __ffma2_rn(h2[q], Wf[q], __fmul2_rn(d2[q], nx));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { P[q] = r2[q]; Wf[q] = __fmul2_rn(r2[q], u2[q]); }
+            snd = Wf[0].x;
+        } else {
+            // r[j] = u[j] (h[j] v[j] + d[j] v[j-1]);  pair (j, j+4) needs (v[j-1], v[j+3]) = pair j-1; j = 0: (inflow, v[3])
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 pv = (q > 0) ? P[(q + 3) & 3] : make_float2(nva, P[3].x);
+                r2[q] = __fmul2_rn(u2[q], __ffma2_rn(h2[q], P[q], __fmul2_rn(d2[q], pv)));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) P[q] = r2[q];
+            snd = P[3].y;
+        }
+        finish(snd);
+    };
 
-        float snd;       // boundary value handed to the neighbour, expressed in 2^Esnd
-        int Esnd;
-        if (k == 0) {
+    if (Tn > 0) {
+        // ---- frame 0 ----
+        ring_sync(0);
+        {
+            float2 u2[4];
+            load_u(u2);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (BETA) { P[q].x = (s0 + q == Sn - 1) ? 1.f : 0.f; P[q].y = (s0 + q + 4 == Sn - 1) ? 1.f : 0.f; }
                 else { P[q].x = (s0 + q == 0) ? u2[q].x : 0.f; P[q].y = 0.f; }
             }
-            snd = BETA ? P[0].x * u2[0].x : P[3].y;
-            Esnd = 0;
-            nv = BETA ? __shfl_down_sync(ASG_FULL_MASK, snd, 1) : __shfl_up_sync(ASG_FULL_MASK, snd, 1);
-            ne = BETA ? __shfl_down_sync(ASG_FULL_MASK, Esnd, 1) : __shfl_up_sync(ASG_FULL_MASK, Esnd, 1);
-            nv *= edge_mask;
-            mymax = BETA ? 0.f : max8(P);
-        } else {
-            // Common exponent of this step.  An empty block adopts its neighbour's exponent; a block far below the
-            // neighbour feeding it is pulled up (own mantissas shrink by fs) so the inflow is always representable.
-            const int pulled = max(Eme, ne - KNB);
-            const int Enew = (mymax == 0.f) ? ne : ((nv > 0.f) ? pulled : Eme);
-            const float fs = Num<T>::exp2i(Eme - Enew);
-            const float nva = nv * Num<T>::exp2i(ne - Enew);
-            const float2 fs2 = make_float2(fs, fs);
-            float2 r2[4];
             if (BETA) {
-                // r[j] = fs * (h[j] w[j] + d[j] w[j+1]);  pair (j, j+4) needs (w[j+1], w[j+5]) = pair j+1; j = 3: (w[4], nv)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 nx = (q < 3) ? Wf[(q + 1) & 3] : make_float2(Wf[0].y, 0.f);
-                    r2[q] = __fmul2_rn(fs2, __ffma2_rn(h2[q], Wf[q], __fmul2_rn(d2[q], nx)));
-                }
-                r2[3].y = fmaf(h2[3].y, Wf[3].y * fs, d2[3].y * nva);
-                if (t < sp) {                                  // band (uniform test): position s is reachable by frame t only if s <= t
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { r2[q].x = (s0 + q > t) ? 0.f : r2[q].x; r2[q].y = (s0 + q + 4 > t) ? 0.f : r2[q].y; }
-                }
-                snd = r2[0].x;                                 // completed with u below
-            } else {
-                // r[j] = (u[j] fs) * (h[j] v[j] + d[j] v[j-1]);  pair (j, j+4) needs (v[j-1], v[j+3]) = pair j-1; j = 0: (nv, v[3])
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 pv = (q > 0) ? P[(q + 3) & 3] : make_float2(0.f, P[3].x);
-                    r2[q] = __fmul2_rn(__fmul2_rn(u2[q], fs2), __ffma2_rn(h2[q], P[q], __fmul2_rn(d2[q], pv)));
-                }
-                r2[0].x = u2[0].x * fmaf(h2[0].x, P[0].x * fs, d2[0].x * nva);
-                const int lb = (Sn - 1) - (Tn - 1 - t);        // band: positions below lb can no longer finish
-                if (lb > 0) {                                  // uniform test
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { r2[q].x = (s0 + q < lb) ? 0.f : r2[q].x; r2[q].y = (s0 + q + 4 < lb) ? 0.f : r2[q].y; }
-                }
-                snd = r2[3].y;
+                for (int q = 0; q < 4; ++q) Wf[q] = __fmul2_rn(P[q], u2[q]);
             }
-            // hand the boundary to the neighbour now (un-normalised, in 2^Enew): the shuffle overlaps the normalisation
-            if (BETA) snd *= u2[0].x;
-            Esnd = Enew;
-            nv = BETA ? __shfl_down_sync(ASG_FULL_MASK, snd, 1) : __shfl_up_sync(ASG_FULL_MASK, snd, 1);
-            ne = BETA ? __shfl_down_sync(ASG_FULL_MASK, Esnd, 1) : __shfl_up_sync(ASG_FULL_MASK, Esnd, 1);
-            nv *= edge_mask;
-            const float m = max8(r2);
-            float sc; int e;
-            pow2_fast(m, sc, e);
-            const float2 sc2 = make_float2(sc, sc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) P[q] = __fmul2_rn(r2[q], sc2);
-            Eme = Enew + e;
-            mymax = m * sc;                                     // alpha: the feed is the state itself
+            finish(BETA ? Wf[0].x : P[3].y);
+            slot_off += slot_bytes;
         }
-        if (BETA) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Wf[q] = __fmul2_rn(P[q], u2[q]);
-            mymax = max8(Wf);
+        // ---- the rest of group 0, whole groups (unrolled over their 8 frames), the last partial group ----
+        int k = 1;
+        for (; k < min(FB, Tn); ++k) { step(); slot_off += slot_bytes; }
+        for (; k + FB <= Tn; k += FB) {
+            ring_sync(k);
+            if ((k & (RING - 1)) == 0) slot_off = 0u;
+#pragma unroll 2
+            for (int j = 0; j < FB; ++j) { step(); slot_off += slot_bytes; }
         }
-
-        if (store) {
-            __stcs(reinterpret_cast<float4 *>(stp), make_float4(P[0].x, P[1].x, P[2].x, P[3].x));
-            __stcs(reinterpret_cast<float4 *>(stp) + 1, make_float4(P[0].y, P[1].y, P[2].y, P[3].y));
-            if (store_e) *esp = Eme;
+        if (k < Tn) {
+            ring_sync(k);
+            if ((k & (RING - 1)) == 0) slot_off = 0u;
+            for (; k < Tn; ++k) { step(); slot_off += slot_bytes; }
         }
-        stp += sstep;
-        esp += estep;
     }
     if (lane == 0) st_volatile_s32(&sm.consumed[0], Tn);
     // ---- score ------------------------------------------------------------------------------------
