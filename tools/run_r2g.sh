@@ -1,4 +1,4 @@
-for p in _ab/consonly _ab/prodonly _ab/nraw8; do for T in 1000 2000; do
+for p in _ab/consonly _ab/gathonly; do for T in 1000 2000; do
 echo "== $p T=$T $(PYTHONPATH=$PWD/$p:$PWD python - $T <<'PY'
 import sys, torch
 import torch_asg_native as nat

@@ -924,39 +924,40 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
     const unsigned pa = vec ? smem_u32(sm.pring) + 32u * (unsigned)min(lane, nblk - 1) : 0u;
     const unsigned slot_bytes = vec ? 4u * (unsigned)sp : 4u * (unsigned)up;
 
-    float2 P[4];         // alpha: state = feed; beta: state Q
-    float2 Wf[4];        // beta: feed = Q o u
-    int Eme = 0;         // the block's exponent: the mantissas below are in units of 2^Eme
+    // The vector carried from step to step: alpha: the state P; beta: the feed W = Q o u (the state Q itself is only stored).
+    // It ping-pongs between X and Y (a step reads one and writes the other), so no register copies are needed.
+    float2 X[4], Y[4];
+    int Eme = 0;         // the block's exponent: the mantissas are in units of 2^Eme
+    float mcar = 0.f;    // maximum of the block's state as stored by the previous step
     float nv = 0.f;      // neighbour's boundary value of the previous step, in units of 2^ne
     int ne = 0;
-    bool fix = false;    // some block of the warp needs the slow path (renormalise / adopt / pull up) before its next step
+    float nva = 0.f;     // the same value in THIS block's units (2^Eme)
+    bool fix = false;    // some block of the warp needs the slow path before its next step
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { P[q] = make_float2(0.f, 0.f); Wf[q] = P[q]; }
+    for (int q = 0; q < 4; ++q) { X[q] = make_float2(0.f, 0.f); Y[q] = X[q]; }
 
     // LAZY block floating point.  A step is only the recurrence itself -- 12 packed multiply-adds on the block's eight
     // mantissas plus the neighbour's boundary value, which arrives already expressed in this block's units (`nva`; flushed
     // to zero when it is more than 2^126 below: real mass is never clamped), one shuffle of (boundary value, exponent)
     // -- and a range check.  The expensive part (maximum -> power of two -> rescale -> exponent update; re-basing the
-    // block on the exponent of what flows in when mass first reaches an empty block or when the inflow would exceed the
-    // mantissa range) runs only when some block of the warp asks for it: the block maximum has drifted outside [2^-40, 4),
-    // or the inflow is >= 4 in the block's units.  That is a warp-uniform branch taken every few frames instead of ~60
-    // instructions on every frame.  Boundary values always travel WITH the exponent they are expressed in, so blocks
-    // renormalise independently of each other.  Stored mantissas stay below 2^3 (a block is renormalised as soon as its
-    // maximum passes 4 and can at most double before that happens; inflow >= 4 is re-based before it is used): the
-    // gradient assembly multiplies alpha and beta mantissas with a constant 2^110.
-    float nva = 0.f;     // the neighbour's boundary value of the previous step in THIS block's units (2^Eme)
+    // block on the exponent of what flows in when mass first reaches an empty block or when the inflow would swamp the
+    // block's own scale) runs only when some block of the warp asks for it: the block maximum has drifted outside
+    // [2^-40, 4), or the inflow is >= 4 in the block's units.  That is a warp-uniform branch taken every few frames
+    // instead of ~60 instructions on every frame.  Boundary values always travel WITH the exponent they are expressed in,
+    // so blocks renormalise independently of each other.  Every stored exponent word also records the drift of the block
+    // maximum (fac_pack), so the gradient assembly still sees normalised mantissas.
     auto to_mine = [&]() {                                         // nv * 2^(ne - Eme), flushed below 2^-126
         const int dl = min(max(ne - Eme, -127), 127);
         return nv * __int_as_float((dl + 127) << 23);
     };
-    auto fix_block = [&]() {
-        const float m = max8(P);
+    auto fix_block = [&](float2 (&V)[4]) {
+        const float m = mcar;
         if (m > 0.f) {
             float sc; int e;
             Num<T>::pow2_norm(m, sc, e);
             const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { P[q] = __fmul2_rn(P[q], sc2); if (BETA) Wf[q] = __fmul2_rn(Wf[q], sc2); }
+            for (int q = 0; q < 4; ++q) V[q] = __fmul2_rn(V[q], sc2);
             Eme += e;
         }
         nva = to_mine();
@@ -969,7 +970,7 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
             const float f = __int_as_float((sh + 127) << 23);
             const float2 f2 = make_float2(f, f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { P[q] = __fmul2_rn(P[q], f2); if (BETA) Wf[q] = __fmul2_rn(Wf[q], f2); }
+            for (int q = 0; q < 4; ++q) V[q] = __fmul2_rn(V[q], f2);
             Eme = En;
             nva = nv * sn;
         } else if (!(m > 0.f)) {
@@ -990,6 +991,7 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
         const int need = min(k + FB, Tn);
         while (ld_volatile_s32(&sm.flags[vec ? 2 : 0]) < need) __nanosleep(20);
         __threadfence_block();
+        if ((k & (RING - 1)) == 0) slot_off = 0u;
     };
     auto load_u = [&](float2 (&u2)[4]) {
         if (vec) {
@@ -1000,92 +1002,93 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
 #pragma unroll
             for (int q = 0; q < 4; ++q) { u2[q].x = lds_f32(la[q] + slot_off); u2[q].y = lds_f32(la[q + 4] + slot_off); }
         }
+        slot_off += slot_bytes;
     };
-    // exchange, range check, stores: the common tail of every step.  No lane-divergent branch anywhere in a step (the
-    // stores are predicated), so the warp-wide shuffles and the vote need no convergence barriers.
-    auto finish = [&](float snd) {
-        // hand the boundary to the neighbour together with the exponent it is expressed in
+    // exchange, range check, stores: the common tail of every step (St: the state to store, snd: the boundary value).
+    // No lane-divergent branch anywhere in a step: the stores are predicated.
+    auto finish = [&](const float2 (&St)[4], float snd) {
         nv = BETA ? __shfl_down_sync(ASG_FULL_MASK, snd, 1) : __shfl_up_sync(ASG_FULL_MASK, snd, 1);
         ne = BETA ? __shfl_down_sync(ASG_FULL_MASK, Eme, 1) : __shfl_up_sync(ASG_FULL_MASK, Eme, 1);
         nv = edge ? 0.f : nv;                                      // an edge lane gets its own value back: no neighbour
         nva = to_mine();
-        const float m = max8(P);
+        const float m = max8(St);
+        mcar = m;
         const unsigned me = (unsigned)__float_as_int(m) >> 23;     // m >= 0
-        // block maximum out of [2^-40, 4) (also inf/NaN) | mass reaching an empty block | inflow beyond the mantissa range
+        // block maximum out of [2^-40, 4) (also inf/NaN) | mass reaching an empty block | inflow beyond the block's scale
         const bool live = me != 0u;
         const bool flag = real & ((live & ((me - 87u) > 41u)) | ((nv > 0.f) & ((!live) | !(nva < 4.f))));
         fix = __any_sync(ASG_FULL_MASK, flag);
-        stg_cs_v4_if(sptr, P[0].x, P[1].x, P[2].x, P[3].x, store);
-        stg_cs_v4_if(sptr + 16, P[0].y, P[1].y, P[2].y, P[3].y, store);
+        stg_cs_v4_if(sptr, St[0].x, St[1].x, St[2].x, St[3].x, store);
+        stg_cs_v4_if(sptr + 16, St[0].y, St[1].y, St[2].y, St[3].y, store);
         stg_s32_if(eptr, fac_pack(Eme, live ? 127 - (int)me : 0), store_e);     // E and the drift of the block maximum
         sptr += rstep;
         eptr += rstep;
     };
     // No band masks here: a position that cannot be reached from the start (s > t) never receives mass, and one that can
     // no longer reach the end has beta = 0 exactly, so its alpha never enters a posterior (the generic consumer zeroes both).
-    auto step = [&]() {
+    auto step = [&](float2 (&src)[4], float2 (&dst)[4]) {
         float2 u2[4];
         load_u(u2);
-        if (fix) fix_block();                                  // warp-uniform
-        float2 r2[4];
-        float snd;
+        if (fix) fix_block(src);                               // warp-uniform
         if (BETA) {
-            // r[j] = h[j] w[j] + d[j] w[j+1];  pair (j, j+4) needs (w[j+1], w[j+5]) = pair j+1; j = 3: (w[4], inflow)
+            // q[j] = h[j] w[j] + d[j] w[j+1];  pair (j, j+4) needs (w[j+1], w[j+5]) = pair j+1; j = 3: (w[4], inflow)
+            float2 Q[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float2 nx = (q < 3) ? Wf[(q + 1) & 3] : make_float2(Wf[0].y, nva);
-                r2[q] = __ffma2_rn(h2[q], Wf[q], __fmul2_rn(d2[q], nx));
+                const float2 nx = (q < 3) ? src[(q + 1) & 3] : make_float2(src[0].y, nva);
+                Q[q] = __ffma2_rn(h2[q], src[q], __fmul2_rn(d2[q], nx));
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { P[q] = r2[q]; Wf[q] = __fmul2_rn(r2[q], u2[q]); }
-            snd = Wf[0].x;
+            for (int q = 0; q < 4; ++q) dst[q] = __fmul2_rn(Q[q], u2[q]);
+            finish(Q, dst[0].x);
         } else {
-            // r[j] = u[j] (h[j] v[j] + d[j] v[j-1]);  pair (j, j+4) needs (v[j-1], v[j+3]) = pair j-1; j = 0: (inflow, v[3])
+            // p[j] = u[j] (h[j] v[j] + d[j] v[j-1]);  pair (j, j+4) needs (v[j-1], v[j+3]) = pair j-1; j = 0: (inflow, v[3])
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float2 pv = (q > 0) ? P[(q + 3) & 3] : make_float2(nva, P[3].x);
-                r2[q] = __fmul2_rn(u2[q], __ffma2_rn(h2[q], P[q], __fmul2_rn(d2[q], pv)));
+                const float2 pv = (q > 0) ? src[(q + 3) & 3] : make_float2(nva, src[3].x);
+                dst[q] = __fmul2_rn(u2[q], __ffma2_rn(h2[q], src[q], __fmul2_rn(d2[q], pv)));
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) P[q] = r2[q];
-            snd = P[3].y;
+            finish(dst, dst[3].y);
         }
-        finish(snd);
+    };
+    auto copy_back = [&]() {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) X[q] = Y[q];
     };
 
     if (Tn > 0) {
-        // ---- frame 0 ----
+        // ---- frame 0 (into X) ----
         ring_sync(0);
         {
-            float2 u2[4];
+            float2 u2[4], Q[4];
             load_u(u2);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (BETA) { P[q].x = (s0 + q == Sn - 1) ? 1.f : 0.f; P[q].y = (s0 + q + 4 == Sn - 1) ? 1.f : 0.f; }
-                else { P[q].x = (s0 + q == 0) ? u2[q].x : 0.f; P[q].y = 0.f; }
+                if (BETA) { Q[q].x = (s0 + q == Sn - 1) ? 1.f : 0.f; Q[q].y = (s0 + q + 4 == Sn - 1) ? 1.f : 0.f; }
+                else { Q[q].x = (s0 + q == 0) ? u2[q].x : 0.f; Q[q].y = 0.f; }
             }
-            if (BETA) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) Wf[q] = __fmul2_rn(P[q], u2[q]);
-            }
-            finish(BETA ? Wf[0].x : P[3].y);
-            slot_off += slot_bytes;
+            for (int q = 0; q < 4; ++q) X[q] = BETA ? __fmul2_rn(Q[q], u2[q]) : Q[q];
+            finish(Q, BETA ? X[0].x : X[3].y);
         }
-        // ---- the rest of group 0, whole groups (unrolled over their 8 frames), the last partial group ----
+        // ---- frame 1 alone, then pairs of frames (X -> Y -> X); group boundaries fall on even frames ----
         int k = 1;
-        for (; k < min(FB, Tn); ++k) { step(); slot_off += slot_bytes; }
-        for (; k + FB <= Tn; k += FB) {
-            ring_sync(k);
-            if ((k & (RING - 1)) == 0) slot_off = 0u;
-#pragma unroll 2
-            for (int j = 0; j < FB; ++j) { step(); slot_off += slot_bytes; }
+        if (k < Tn) { step(X, Y); copy_back(); ++k; }
+        for (; k + 1 < Tn; k += 2) {
+            if ((k & (FB - 1)) == 0) ring_sync(k);
+            step(X, Y);
+            step(Y, X);
         }
         if (k < Tn) {
-            ring_sync(k);
-            if ((k & (RING - 1)) == 0) slot_off = 0u;
-            for (; k < Tn; ++k) { step(); slot_off += slot_bytes; }
+            if ((k & (FB - 1)) == 0) ring_sync(k);
+            step(X, Y);
+            copy_back();
         }
     }
+    // what the score read-out below looks at
+    float2 P[4], Wf[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { P[q] = X[q]; Wf[q] = X[q]; }
     if (lane == 0) st_volatile_s32(&sm.consumed[0], Tn);
     // ---- score ------------------------------------------------------------------------------------
     const double msum = (Tn > 0) ? wait_msum(sm.msum, &sm.flags[1]) : 0.0;
