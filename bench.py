@@ -384,7 +384,8 @@ def run_b200(args):
     # Roofline kernel, timed LIVE inside the timed region: every PROF_STRIDE-th step runs the same zero-allocation calls
     # eagerly (graph replays cannot carry the library's event pairs) with an event pair around that one kernel on its
     # launching stream.  The other steps are graph replays.
-    roof_kernel = "grad_kernel" if not fwd_only else "fac_scan_kernel"
+    large = L > 64                               # large alphabets: the FCC scans (a dense product per frame) dominate: fp32-FMA bound
+    roof_kernel = "fcc_scan_kernel" if large else ("grad_kernel" if not fwd_only else "fac_scan_kernel")
     lib.asg_profile_select(ctypes.c_uint(1 << kid[roof_kernel]))
     PROF_STRIDE = int(os.environ.get("ASG_BENCH_STRIDE", "8"))      # 0: no eager steps in the timed loop (developer)
     if world > 1:
@@ -489,7 +490,8 @@ def run_b200(args):
                 "step": "GraphedASGLoss.step: forward+backward+all-reduce as one graph replay (no autograd graph)",
                 "eager": "ASGLoss(...)(...) + loss.backward() (eager autograd, per-call allocations)"}[args.api]
     out = {
-        "metric": METRIC, "value": N * world * args.steps / (ms * 1e-3), "unit": "utterances/s", "n_gpus": world,
+        "metric": METRIC if args.workload in ("cfg2", "cfg5") else METRIC + " [workload %s]" % args.workload,
+        "value": N * world * args.steps / (ms * 1e-3), "unit": "utterances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "host_issue_ms_per_step": host_ms,
         "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -511,7 +513,17 @@ def run_b200(args):
     except Exception:
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    if "grad_kernel" in kernels:
+    if large and "fcc_scan_kernel" in kernels:
+        # one launch = alpha and beta scans of the whole batch: 2 directions x (T-1) frames x one [L x L] x [L x N] product
+        flops = 2.0 * (T - 1) * 2.0 * L * L * N          # 2 directions x (T-1) frames x 2 L^2 N flops
+        ach = flops / (kernels["fcc_scan_kernel"]["avg_us"] * 1e-6) / 1e12
+        fpeak = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+        out["roofline"] = {"bound": "fp32_fma", "kernel": "fcc_scan_kernel (resident-tile scan: one dense [LxL]x[LxN] product per frame and direction)",
+                           "achieved": ach, "peak": fpeak, "unit": "TFLOP/s", "frac": ach / fpeak, "traffic": None,
+                           "algorithmic_flops": flops, "avg_us": kernels["fcc_scan_kernel"]["avg_us"],
+                           "peak_source": "nominal fp32 FMA peak: 148 SMs x 128 lanes x 2 x max SM clock (MEASURED_PEAKS.json holds no fp32 figure); "
+                                          "tensor cores are not used: the path is specified in fp32"}
+    elif "grad_kernel" in kernels:
         alg = grad_alg_bytes(T, N, L, S)
         ach = alg / (kernels["grad_kernel"]["avg_us"] * 1e-6) / 1e9
         traffic = None

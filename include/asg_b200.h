@@ -104,6 +104,7 @@ typedef struct asg_layout {
     size_t off_ehat_t;        /* [L,L]       transpose of ehat           (L > 64 only, else = off_ehat)   */
     size_t off_fmax;          /* [N,tp]      per-frame emission maxima   (L > 64 only)                   */
     size_t off_rmax;          /* [1]         max A                       (L > 64 only)                   */
+    size_t off_large_ws;      /* state exchange, maxima, barrier counters of the large-alphabet FCC scan (L > 64 only) */
 } asg_layout_t;
 
 /* Fills *out.  Returns ASG_E_UNSUPPORTED for shapes this build does not cover. */

@@ -51,7 +51,7 @@ class Layout(ctypes.Structure):
         (n, ctypes.c_size_t) for n in ("elem_bytes", "rec_bytes", "state_bytes", "ctx_bytes", "grad_scratch_bytes",
                                        "rec_fac_alpha", "rec_fac_beta", "rec_fac_ea", "rec_fac_eb", "rec_fcc_alpha",
                                        "rec_fcc_beta", "rec_fcc_w", "rec_fcc_scale",
-                                       "off_ehat", "off_fac_hd", "off_lengths", "off_scalars", "off_ehat_t", "off_fmax", "off_rmax")]
+                                       "off_ehat", "off_fac_hd", "off_lengths", "off_scalars", "off_ehat_t", "off_fmax", "off_rmax", "off_large_ws")]
 
 
 def _layout(lib, dt, T, N, L, S):

@@ -53,7 +53,7 @@ def build_lib(verbose=False):
             raise RuntimeError("nvcc failed on " + src)
     if procs or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + [
-               "-cudart", "shared", "-lcublas", "-ccbin", CXX,
+               "-cudart", "shared", "-ccbin", CXX,
                "-Xlinker", "-rpath," + os.path.join(CUDA_HOME, "lib64")]
         if verbose:
             print(" ".join(cmd), flush=True)

@@ -207,13 +207,15 @@ int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout
         out->off_ehat_t = take(eb * (size_t)L * L);
         out->off_fmax = take(eb * (size_t)N * out->tp);
         out->off_rmax = take(eb);
+        out->off_large_ws = take(large_ws_bytes(eb, N, L));
     }
     out->ctx_bytes = off;
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) device = -1;
     out->grad_scratch_bytes = align_up(eb * (size_t)grad_grid_size(device) * L * L, 256);
     if (L > ASG_SMALL_L)   // G [L,L] + the FAC edge sums [2,N,sp] in 64-bit fixed point
-        out->grad_scratch_bytes = align_up(eb * (size_t)L * L, 256) + align_up(16 * (size_t)N * out->sp, 256);
+        out->grad_scratch_bytes = align_up(eb * (size_t)large_splitk_host((int)L) * L * L, 256) + align_up(16 * (size_t)N * out->sp, 256) +
+                                  align_up(8 * (size_t)L * L, 256);
     return 0;
 }
 
@@ -470,7 +472,7 @@ int asg_profile_read(int kernel_id, double *total_ms, uint64_t *launches) {
     return 0;
 }
 const char *asg_kernel_name(int kernel_id) {
-    static const char *names[K_COUNT] = {"fcc_scan_kernel", "fac_scan_kernel", "grad_kernel", "grad_finalize_kernel", "host_misc"};
+    static const char *names[K_COUNT] = {"fcc_scan_kernel", "fac_scan_kernel", "grad_kernel", "grad_finalize_kernel", "host_misc", "grad_large_gemm_kernel"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "";
 }
 int asg_kernel_count(void) { return K_COUNT; }

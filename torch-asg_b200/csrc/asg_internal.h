@@ -16,6 +16,7 @@ template <typename T> struct Ctx {
     T *ehat_t;        // [L,L]  transpose (large alphabets only)
     T *fmax;          // [N,tp] per-frame emission maxima (large alphabets only)
     T *rmax;          // [1]    max A (large alphabets only)
+    char *large_ws;   // workspace of the resident-tile FCC scan (large alphabets only, asg_large.cu)
     T *fac_hd;        // [2,N,sp]   h_s, d_s (edge s -> s+1)
     int64_t *il;      // [N]
     int64_t *tl;      // [N]
@@ -47,6 +48,7 @@ template <typename T> inline Ctx<T> make_ctx(void *state, void *blob, const asg_
     c.ehat_t = reinterpret_cast<T *>(b + lay.off_ehat_t);
     c.fmax = reinterpret_cast<T *>(b + lay.off_fmax);
     c.rmax = reinterpret_cast<T *>(b + lay.off_rmax);
+    c.large_ws = lay.off_large_ws ? b + lay.off_large_ws : nullptr;
     c.fac_hd = reinterpret_cast<T *>(b + lay.off_fac_hd);
     c.il = reinterpret_cast<int64_t *>(b + lay.off_lengths);
     c.tl = c.il + N;
@@ -109,11 +111,13 @@ template <typename T> int large_prepare(const ScanArgs<T> &a, cudaStream_t strea
 template <typename T> int launch_fcc_large(const ScanArgs<T> &a, int ndirs, cudaStream_t stream);
 template <typename T> int launch_grad_large(const GradArgs<T> &a, int parts, cudaStream_t stream);
 int grad_grid_size(int device);   // number of persistent CTAs asg_grad launches
+int large_splitk_host(int L);
+size_t large_ws_bytes(size_t elem_bytes, int64_t N, int64_t L);   // asg_large.cu     // K splits of the large-alphabet transition-gradient contraction (asg_large.cu)
 void count_launch(int n = 1);
 void release_side_slots();          // asg_scan.cu: asg_release()
 
 // kernel ids for the launch counter / live profiler (asg_profile_* in include/asg_b200.h)
-enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_COUNT = 5 };
+enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_GRAD_GEMM = 5, K_COUNT = 6 };
 
 // RAII: counts one launch of kernel `kid` and, while profiling is enabled, brackets it with a pair
 // of CUDA events recorded on the launching stream (read back by asg_profile_read()).
