@@ -200,6 +200,43 @@ int asg_backward(int dtype, const void *g, int64_t g_stride, double scale,
                  void *grad_x, void *grad_A, void *scratch,
                  asg_stream_t stream);
 
+/*
+ * Fused log_softmax + ASG (the reference's users feed log_softmax'ed activations, test/test_asg.py:111-113).
+ * The loss needs no separate normalisation pass at all: loss(log_softmax(z)) == loss(z), because the fully-connected score IS the
+ * per-frame normaliser (both scores shift by the same sum of log-partition values), so asg_scan / asg_forward / asg_step are simply
+ * run on the raw activations z.  The gradient is d loss / d z = gx - softmax(z) * sum_l gx, and sum_l gx[t,n,:] is exactly zero for
+ * every utterance that has a valid alignment; only an infeasible utterance (aligned score -inf, loss +inf) needs the softmax term.
+ * This call applies it in place to grad_x [T,N,L] (as written by asg_grad / asg_backward / asg_step for the same z): one tiny launch
+ * whose CTAs leave at once for feasible utterances.  g / g_stride / scale: the upstream gradient of utterance n's loss,
+ * scale * g[n * g_stride] (g == NULL reads as 1).  Saves, against log_softmax + ASG, one read and one write of [T,N,L] in the
+ * forward pass and two reads and one write in the backward pass.
+ */
+int asg_logits_backward_fix(int dtype,
+                            const void *z, int64_t z_st, int64_t z_sn, int64_t z_sl,
+                            const void *aligned_scores,
+                            const void *g, int64_t g_stride, double scale,
+                            const int64_t *il,
+                            int64_t T, int64_t N, int64_t L,
+                            void *grad_x,
+                            asg_stream_t stream);
+
+/*
+ * Viterbi forced alignment ("Viterbi decoders" is an open TODO of the reference, README.md:33): the
+ * force-aligned lattice (force_aligned_lattice.cpp:84-111, doc/tech_report.tex:221-229) in the tropical semiring
+ * (tech_report.tex:84-87, max instead of log-sum-exp).  scores[n] = the best path's score (dtype; -inf when the target does
+ * not fit), path[n,t] = the target position aligned to frame t (int64, -1 on padding frames and infeasible utterances);
+ * ties prefer staying on the current position.  scratch: asg_viterbi_scratch_bytes(T, N, S) bytes (back-pointer bits).
+ */
+size_t asg_viterbi_scratch_bytes(int64_t T, int64_t N, int64_t S);
+int asg_viterbi(int dtype,
+                const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl,
+                const void *A, int64_t A_s0, int64_t A_s1,
+                const int64_t *y, int64_t y_s0, int64_t y_s1,
+                const int64_t *il, const int64_t *tl,
+                int64_t T, int64_t N, int64_t L, int64_t S,
+                void *scores, int64_t *path, void *scratch,
+                asg_stream_t stream);
+
 /* ---- host-buffer convenience API (end-to-end path) ------------------------------------------- */
 typedef struct asg_host_ctx asg_host_ctx_t;
 

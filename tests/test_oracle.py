@@ -115,3 +115,27 @@ def test_oracle_matches_live_reference():
     ref = ref_driver.ref_asg(x, y, A, il, tl, g)
     mine = O.asg_loss(x, y, A, il, tl, g)
     _check_against({"ref_" + k: v for k, v in ref.items()}, mine)
+
+
+def test_viterbi_oracle_against_brute_force():
+    """The Viterbi restatement (oracle/asg_oracle.py: viterbi_align) against an exhaustive search over every monotone alignment."""
+    import itertools
+    rng = np.random.default_rng(5)
+    for T, S, L in [(5, 3, 4), (6, 1, 3), (4, 4, 5), (7, 4, 3)]:
+        x = rng.standard_normal((T, 1, L))
+        A = rng.standard_normal((L, L))
+        y = rng.integers(0, L, (1, S))
+        best, best_path = -np.inf, None
+        for moves in itertools.combinations(range(1, T), S - 1):          # the frames at which the alignment advances
+            pos = np.zeros(T, dtype=int)
+            for m in moves:
+                pos[m:] += 1
+            lab = y[0][pos]
+            sc = x[np.arange(T), 0, lab].sum() + sum(A[lab[t], lab[t - 1]] for t in range(1, T))
+            if sc > best:
+                best, best_path = sc, pos
+        s, p = O.viterbi_align(x, y, A)
+        assert abs(s[0] - best) < 1e-12 and (p[0] == best_path).all()
+    # infeasible and empty cases
+    s, p = O.viterbi_align(rng.standard_normal((6, 1, 4)), rng.integers(0, 4, (1, 5)), rng.standard_normal((4, 4)), np.array([3]), np.array([5]))
+    assert np.isneginf(s[0]) and (p == -1).all()

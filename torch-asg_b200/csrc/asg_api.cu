@@ -168,6 +168,35 @@ template <typename T> __global__ void __launch_bounds__(256) losses_kernel(const
     write_losses_block<T>(full, aligned, losses, N, tail, red8, true, scale);
 }
 
+// Fused log_softmax + ASG, backward side.  loss(log_softmax(z)) == loss(z) (the FCC term IS the per-frame normaliser: both scores
+// shift by the same sum of log-partition values) and d loss / d z = gx - softmax(z) * sum_l gx, where sum_l gx[t,n,:] is exactly 0
+// for every utterance with a valid alignment (the two posteriors cancel) and g_n for an infeasible one (aligned = -inf: its FAC
+// gradients are exactly 0, force_aligned_lattice.cpp:164-168 masked softmax).  So only infeasible utterances need a correction:
+// one CTA per utterance, which leaves at once unless its aligned score is -inf; one warp per frame otherwise.
+template <typename T>
+__global__ void __launch_bounds__(256) logits_fix_kernel(const T *z, int64_t z_st, int64_t z_sn, int64_t z_sl, const T *aligned, const T *g,
+                                                         int64_t g_stride, T scale, const int64_t *il, int Tt, int N, int L, T *grad_x) {
+    const int n = blockIdx.x;
+    const T al = aligned[n];
+    if (al > Num<T>::neg_inf()) return;
+    const T gn = g ? scale * g[(int64_t)n * g_stride] : scale;
+    int Tn = il ? (int)il[n] : Tt;
+    Tn = max(0, min(Tn, Tt));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = warp; t < Tn; t += 8) {
+        const T *row = z + (int64_t)t * z_st + (int64_t)n * z_sn;
+        T m = Num<T>::neg_inf();
+        for (int l = lane; l < L; l += 32) m = tmax(m, row[(int64_t)l * z_sl]);
+        m = Num<T>::warp_max(m);
+        if (!(m > Num<T>::neg_inf())) continue;
+        T sum = T(0);
+        for (int l = lane; l < L; l += 32) sum += Num<T>::exp_(row[(int64_t)l * z_sl] - m);
+        sum = warp_sum(sum);
+        T *gx = grad_x + ((int64_t)t * N + n) * L;
+        for (int l = lane; l < L; l += 32) gx[l] -= gn * (Num<T>::exp_(row[(int64_t)l * z_sl] - m) / sum);
+    }
+}
+
 extern "C" {
 
 int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout_t *out) {
@@ -295,6 +324,41 @@ int asg_backward(int dtype, const void *g, int64_t g_stride, double scale, const
         e = grad_typed<double>(ASG_PART_BOTH, g, g_stride, g, g_stride, state, ctx, y, y_s0, y_s1, lay, T, N, L, S, grad_x, grad_A, scratch,
                                (cudaStream_t)stream, &ex);
     return cuda_fail(e, "asg_backward");
+}
+
+int asg_logits_backward_fix(int dtype, const void *z, int64_t z_st, int64_t z_sn, int64_t z_sl, const void *aligned_scores, const void *g,
+                            int64_t g_stride, double scale, const int64_t *il, int64_t T, int64_t N, int64_t L, void *grad_x,
+                            asg_stream_t stream) {
+    if (dtype != ASG_F32 && dtype != ASG_F64) return fail(ASG_E_DTYPE, "dtype must be ASG_F32 or ASG_F64, got %d", dtype);
+    if (!z || !aligned_scores || !grad_x) return fail(ASG_E_NULL, "asg_logits_backward_fix: z, aligned_scores and grad_x are required");
+    if (T <= 0 || N <= 0 || L <= 0) return fail(ASG_E_SHAPE, "asg_logits_backward_fix: T, N, L must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        LaunchScope ls(K_HOST_MISC, st);
+        if (dtype == ASG_F32)
+            logits_fix_kernel<float><<<(unsigned)N, 256, 0, st>>>((const float *)z, z_st, z_sn, z_sl, (const float *)aligned_scores, (const float *)g,
+                                                                   g_stride, (float)scale, il, (int)T, (int)N, (int)L, (float *)grad_x);
+        else
+            logits_fix_kernel<double><<<(unsigned)N, 256, 0, st>>>((const double *)z, z_st, z_sn, z_sl, (const double *)aligned_scores, (const double *)g,
+                                                                    g_stride, scale, il, (int)T, (int)N, (int)L, (double *)grad_x);
+    }
+    return cuda_fail((int)cudaGetLastError(), "asg_logits_backward_fix");
+}
+
+size_t asg_viterbi_scratch_bytes(int64_t T, int64_t N, int64_t S) {
+    if (T <= 0 || N <= 0 || S <= 0) return 0;
+    return align_up(sizeof(unsigned) * (size_t)N * T * viterbi_words(S), 256);
+}
+
+int asg_viterbi(int dtype, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0, int64_t A_s1, const int64_t *y,
+                int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl, int64_t T, int64_t N, int64_t L, int64_t S, void *scores,
+                int64_t *path, void *scratch, asg_stream_t stream) {
+    if (dtype != ASG_F32 && dtype != ASG_F64) return fail(ASG_E_DTYPE, "dtype must be ASG_F32 or ASG_F64, got %d", dtype);
+    if (T <= 0 || N <= 0 || L <= 0 || S <= 0) return fail(ASG_E_SHAPE, "asg_viterbi: T, N, L, S must be positive");
+    if (S > 4096) return fail(ASG_E_UNSUPPORTED, "asg_viterbi covers S <= 4096 target positions (got %lld)", (long long)S);
+    if (!x || !A || !y || !scores || !path || !scratch) return fail(ASG_E_NULL, "asg_viterbi: x, A, y, scores, path and scratch are required");
+    return cuda_fail(viterbi_dispatch(dtype, x, x_st, x_sn, x_sl, A, A_s0, A_s1, y, y_s0, y_s1, il, tl, T, N, L, S, scores, path, scratch,
+                                      (cudaStream_t)stream), "asg_viterbi");
 }
 
 int asg_step(int dtype, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0, int64_t A_s1,

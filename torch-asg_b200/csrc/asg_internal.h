@@ -115,6 +115,11 @@ int large_splitk_host(int L);
 size_t large_ws_bytes(size_t elem_bytes, int64_t N, int64_t L);   // asg_large.cu     // K splits of the large-alphabet transition-gradient contraction (asg_large.cu)
 void count_launch(int n = 1);
 void release_side_slots();          // asg_scan.cu: asg_release()
+// asg_viterbi.cu
+int viterbi_words(int64_t S);
+int viterbi_dispatch(int dtype, const void *x, int64_t x_st, int64_t x_sn, int64_t x_sl, const void *A, int64_t A_s0, int64_t A_s1,
+                     const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *il, const int64_t *tl, int64_t T, int64_t N, int64_t L,
+                     int64_t S, void *scores, int64_t *path, void *scratch, cudaStream_t st);
 
 // kernel ids for the launch counter / live profiler (asg_profile_* in include/asg_b200.h)
 enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_GRAD_GEMM = 5, K_COUNT = 6 };

@@ -309,6 +309,41 @@ struct Workspace {
     }
 };
 
+// not in the reference: the backward correction of the fused log_softmax + ASG path (asg_logits_backward_fix)
+void logits_backward_fix(Tensor &z, Tensor &aligned, Tensor &g, double scale, Tensor &input_lengths, Tensor &grad_x) {
+    check_cuda(z, "inputs");
+    TORCH_CHECK(z.dim() == 3 && grad_x.dim() == 3 && grad_x.is_contiguous() && grad_x.sizes() == z.sizes() && grad_x.scalar_type() == z.scalar_type(),
+                "grad_x must be a contiguous tensor shaped like inputs");
+    const int64_t T = z.size(0), N = z.size(1), L = z.size(2);
+    TORCH_CHECK(aligned.numel() == N && aligned.is_contiguous() && aligned.scalar_type() == z.scalar_type() && aligned.device() == z.device(),
+                "aligned scores must be [N] in the inputs' dtype");
+    TORCH_CHECK(g.numel() == 1 || g.numel() == N, "grad must hold 1 or N elements");
+    c10::cuda::CUDAGuard guard(z.device());
+    Tensor il = as_device_long(input_lengths, z, "input_lengths", N);
+    Tensor gg = g.to(z.options()).contiguous();
+    check_rc(asg_logits_backward_fix(dtype_code(z, "inputs"), z.data_ptr(), z.stride(0), z.stride(1), z.stride(2), aligned.data_ptr(), gg.data_ptr(),
+                                     gg.numel() == 1 ? 0 : 1, scale, il.data_ptr<int64_t>(), T, N, L, grad_x.data_ptr(), current_stream()));
+}
+
+// not in the reference (README.md:33 lists it as to do): Viterbi forced alignment, asg_viterbi
+std::tuple<Tensor, Tensor> viterbi_align(Tensor &inputs, Tensor &targets, Tensor &transition, Tensor &input_lengths, Tensor &target_lengths) {
+    TORCH_CHECK(inputs.dim() == 3 && targets.dim() == 2 && targets.size(0) == inputs.size(1), "inputs [T,N,L], targets [N,S]");
+    const int64_t T = inputs.size(0), N = inputs.size(1), L = inputs.size(2), S = targets.size(1);
+    check_inputs(inputs, transition, T, N, L);
+    c10::cuda::CUDAGuard guard(inputs.device());
+    const int dt = dtype_code(inputs, "inputs");
+    Tensor y = as_device_long(targets, inputs, "targets", N * S);
+    Tensor il = as_device_long(input_lengths, inputs, "input_lengths", N);
+    Tensor tl = as_device_long(target_lengths, inputs, "target_lengths", N);
+    Tensor scores = at::empty({N}, inputs.options().requires_grad(false));
+    Tensor path = at::empty({N, T}, inputs.options().dtype(at::kLong).requires_grad(false));
+    Tensor scratch = bytes_like(inputs, asg_viterbi_scratch_bytes(T, N, S));
+    check_rc(asg_viterbi(dt, inputs.data_ptr(), inputs.stride(0), inputs.stride(1), inputs.stride(2), transition.data_ptr(), transition.stride(0),
+                         transition.stride(1), y.data_ptr<int64_t>(), y.stride(0), y.stride(1), il.data_ptr<int64_t>(), tl.data_ptr<int64_t>(),
+                         T, N, L, S, scores.data_ptr(), path.data_ptr<int64_t>(), scratch.data_ptr(), current_stream()));
+    return {scores, path};
+}
+
 // ---- extras (not in the reference): introspection for tests and bench.py ------------------------
 Tensor ctx_scalars(Tensor &ctx, bool is_double, int64_t T, int64_t N, int64_t L, int64_t S) {
     const asg_layout_t lay = layout_of(is_double ? ASG_F64 : ASG_F32, T, N, L, S);
@@ -347,6 +382,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def_readonly("state", &Workspace::state)
         .def_readonly("ctx", &Workspace::ctx)
         .def_readonly("T", &Workspace::T).def_readonly("N", &Workspace::N).def_readonly("L", &Workspace::L).def_readonly("S", &Workspace::S);
+    m.def("viterbi_align", &viterbi_align, "Viterbi forced alignment: (scores[N], path[N,T]) (not in the reference)");
+    m.def("logits_backward_fix", &logits_backward_fix,
+          "fused log_softmax + ASG: in-place correction of grad_x for infeasible utterances (not in the reference)");
     m.def("_ctx_scalars", &ctx_scalars, "per-utterance float64 bookkeeping [N,8] of a context blob");
     m.def("_launch_count", []() { return asg_launch_count(); }, "kernels launched by libasg_b200 so far");
     m.def("_version", []() { return std::string(asg_version()); });
