@@ -221,6 +221,23 @@ int asg_logits_backward_fix(int dtype,
                             asg_stream_t stream);
 
 /*
+ * Range report.  The recursions run in the real domain (FCC) / in block floating point (FAC), not in the reference's log domain:
+ * inside one frame (FCC: against the frame's maximum emission; FAC: inside one block of 8 target positions) entries more than
+ * the format's range apart (fp32: 2^126 ~ 87 nats, fp64: 2^1022 ~ 708 nats) cannot coexist, and the smaller one is flushed to
+ * ZERO (never clamped to the smallest normal number).  For normalised inputs (log-probabilities of a network) that never
+ * matters; for extremely peaked inputs it can, and the kernels say so instead of returning a silently wrong gradient:
+ * flags[n] (device int32 [N]) is the OR of
+ *   1  a finite emission underflowed against its frame's maximum (exp(x - max) == 0),
+ *   2  in some frame a block of 8 target positions could hold flushed entries whose alpha*beta product is not negligible (below
+ *      2^-24) against the frame's largest product: posterior mass may have been lost,
+ *   4  the aligned score of a feasible utterance came out as -inf.
+ * Bits 1 and 4 are final after asg_scan / asg_forward, bit 2 after asg_grad / asg_backward / asg_step on the same ctx.  A caller
+ * that sees a flag should rerun that batch in ASG_F64 (same API, 8x the range).
+ */
+int asg_range_flags(int dtype, const void *state, const void *ctx, int64_t T, int64_t N, int64_t L, int64_t S, int32_t *flags,
+                    asg_stream_t stream);
+
+/*
  * Viterbi forced alignment ("Viterbi decoders" is an open TODO of the reference, README.md:33): the
  * force-aligned lattice (force_aligned_lattice.cpp:84-111, doc/tech_report.tex:221-229) in the tropical semiring
  * (tech_report.tex:84-87, max instead of log-sum-exp).  scores[n] = the best path's score (dtype; -inf when the target does

@@ -15,6 +15,12 @@ u_t = exp(x[t] - m_t):
 and the bidiagonal analogue for FAC with h_s = exp(A[y_s,y_s]-Rb), d_s = exp(A[y_{s+1},y_s]-Rb).
 FAC states outside the feasible band (tech_report.tex:214: s <= t and S-1-s <= T-1-t) carry no
 complete path; they are set to exactly 0 so the per-frame rescale follows the band's maximum.
+
+This model renormalises every block on every frame.  The fp32 kernels do it lazily (only when a block maximum leaves
+[2^-40, 4) or the inflow from the neighbour would swamp the block) and record the drift in the exponent word: the same values
+up to exact powers of two.  Range rules shared with the kernels: a value more than the format's range (2^126 in fp32, 2^1022 in
+fp64) below the scale it is brought to is FLUSHED to zero, never clamped to the smallest normal number; a block re-bases on what
+flows in from its neighbour when that inflow would be >= 4 in the block's own units (or the block is empty).
 """
 import numpy as np
 
@@ -108,24 +114,41 @@ def asg_scaled(x, y, A, il, tl, g_full, g_aligned, dtype=np.float32):
             sc, e = _pow2_scale(vb.max(1), dt)
             return (vb * sc[:, None]).reshape(Sp).astype(dt), ex + e.astype(np.int64)
 
+        lim = 126 if dt == np.float32 else 1022          # the format's normal range in powers of two (kernel: Num<T>::kMaxShift)
+
         def shift(val, de):
-            """val * 2^de with de clamped like the kernel does"""
-            return (val * np.exp2(np.clip(de, -126, 126)).astype(dt)).astype(dt)
+            """val * 2^de the way the kernels do it: more than the format's range below is FLUSHED to zero (never clamped to the
+            smallest normal number: that would inject mass), above it saturates at 2^lim."""
+            de = np.asarray(de)
+            f = np.where(de < -lim, 0.0, np.exp2(np.clip(de, -lim, lim)))
+            return (val * f.astype(dt)).astype(dt)
+
+        def rebase(prev, ex, e_nb, v_nb, b):
+            """Block b receives v_nb * 2^e_nb from its neighbour.  An empty block adopts the exponent of what arrives; a block whose
+            inflow would be >= 4 in its own units is re-based on the inflow (its own mantissas shrink, flushed below the range)."""
+            if v_nb <= 0:
+                return
+            blk = prev[b * BLK:(b + 1) * BLK]
+            nva = float(v_nb) * 2.0 ** float(np.clip(e_nb - ex[b], -lim, lim))
+            if blk.max() == 0 or nva >= 4.0:
+                en = int(np.floor(np.log2(float(v_nb))))
+                En = int(e_nb) + en
+                prev[b * BLK:(b + 1) * BLK] = shift(blk, np.full(BLK, min(int(ex[b]) - En, 0)))
+                ex[b] = En
 
         Pa = np.zeros((Tn, Sp), dtype=dt); Ea = np.zeros((Tn, nb), dtype=np.int64)
         v = np.zeros(Sp, dtype=dt); v[0] = ubp[0, 0]
         Pa[0], Ea[0] = renorm(v, np.zeros(nb, dtype=np.int64))
         for t in range(1, Tn):
             ex = Ea[t - 1].copy()
-            prev = Pa[t - 1]
-            empty = prev.reshape(nb, BLK).max(1) == 0
-            for b in range(1, nb):                                   # an all-zero block adopts its left neighbour's exponent
-                if empty[b]:
-                    ex[b] = ex[b - 1] if not empty[b - 1] else ex[b]
+            prev = Pa[t - 1].copy()
+            for b in range(1, nb):                                   # adopt / re-base on what flows in from the left block
+                rebase(prev, ex, Ea[t - 1][b - 1], Pa[t - 1][b * BLK - 1], b)
             left = np.zeros(Sp, dtype=dt)
             left[1:] = prev[:-1]
+            left[BLK::BLK] = Pa[t - 1][BLK - 1:Sp - 1:BLK]           # block-boundary elements come from the left block AS IT WAS
             de = np.zeros(Sp, dtype=np.int64)
-            de[BLK::BLK] = Ea[t - 1][:-1] - ex[1:]                   # block-boundary elements come from the left block
+            de[BLK::BLK] = Ea[t - 1][:-1] - ex[1:]
             left = shift(left, de)
             v = ubp[t] * (hp * prev + np.concatenate([[0], dp[:-1]]).astype(dt) * left)
             v[:max(0, (Sn - 1) - (Tn - 1 - t))] = 0                  # band: states that can no longer reach the end
@@ -134,14 +157,14 @@ def asg_scaled(x, y, A, il, tl, g_full, g_aligned, dtype=np.float32):
         Qa[Tn - 1, Sn - 1] = 1
         msum = 0.0
         for t in range(Tn - 2, -1, -1):
-            W = ubp[t + 1] * Qa[t + 1]
+            W0 = (ubp[t + 1] * Qa[t + 1]).astype(dt)
+            W = W0.copy()
             ex = Eb[t + 1].copy()
-            empty = W.reshape(nb, BLK).max(1) == 0
-            for b in range(nb - 2, -1, -1):
-                if empty[b]:
-                    ex[b] = ex[b + 1] if not empty[b + 1] else ex[b]
+            for b in range(nb - 2, -1, -1):                          # adopt / re-base on what flows in from the right block
+                rebase(W, ex, Eb[t + 1][b + 1], W0[(b + 1) * BLK], b)
             right = np.zeros(Sp, dtype=dt)
             right[:-1] = W[1:]
+            right[BLK - 1:Sp - 1:BLK] = W0[BLK::BLK]                 # block-boundary elements come from the right block AS IT WAS
             de = np.zeros(Sp, dtype=np.int64)
             de[BLK - 1:Sp - 1:BLK] = Eb[t + 1][1:] - ex[:-1]
             right = shift(right, de)
@@ -156,7 +179,8 @@ def asg_scaled(x, y, A, il, tl, g_full, g_aligned, dtype=np.float32):
         prod = (Pa * Qa).reshape(Tn, nb, BLK)
         live = prod.max(2) > 0
         Cmax = np.where(live, C, -10**9).max(1)                      # [Tn]
-        wgt = np.where(live, np.exp2(np.clip(C - Cmax[:, None], -126, 0)), 0).astype(dt)
+        dC = C - Cmax[:, None]
+        wgt = np.where(live & (dC >= -lim), np.exp2(np.clip(dC, -lim, 0)), 0).astype(dt)        # flushed, not clamped
         gam = (prod * wgt[:, :, None]).reshape(Tn, Sp)
         Z = gam.sum(-1); ok = Z > 0; Zs = np.where(ok, Z, 1)
         post = (g_aligned[n] * gam / Zs[:, None] * ok[:, None]).astype(dt)   # [Tn,Sp]
@@ -170,8 +194,8 @@ def asg_scaled(x, y, A, il, tl, g_full, g_aligned, dtype=np.float32):
         move = np.concatenate([[0], dp[:-1]]).astype(dt)[None, :] * leftm
         den = stay + move
         with np.errstate(invalid="ignore", divide="ignore"):
-            frac = np.where(den > 0, stay / den, 0)
-            fracm = np.where(den > 0, move / den, 0)
+            frac = np.where(den > 0, stay / den, 0)        # share of the mass that stayed; the rest moved (as the kernels do:
+            fracm = 1.0 - frac                              # the move share is what is left, never a second quotient)
         gH = (post[1:] * frac).sum(0)
         gD = (post[1:] * fracm).sum(0)                              # gD[s] = edge (s-1 -> s)
         for s_ in range(Sn):

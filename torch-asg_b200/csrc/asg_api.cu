@@ -197,6 +197,56 @@ __global__ void __launch_bounds__(256) logits_fix_kernel(const T *z, int64_t z_s
     }
 }
 
+__global__ void range_flags_kernel(const double *scalars, int N, int *out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) out[n] = *reinterpret_cast<const int *>(scalars + (size_t)n * 8 + SC_FLAGS);
+}
+
+// The gradient assembly's view of the stored force-aligned states, re-read on demand: flag the utterances in which a block of
+// target positions may hold flushed entries that matter (RF_POSTERIOR_THIN; the criterion is fac_block_at_risk()).  One warp per
+// frame, the frame's blocks strided over the lanes, two passes (largest product of the frame, then the check).
+template <typename T>
+__global__ void __launch_bounds__(128) range_check_kernel(Ctx<T> ctx, int N, int *out) {
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Tn = (int)ctx.il[n], Sn = (int)ctx.tl[n];
+    if (Sn > Tn || Tn <= 0) return;                         // infeasible: no posterior
+    const int nblk = (Sn + 7) / 8;
+    bool risk = false;
+    for (int t = blockIdx.x * 4 + warp; t < Tn; t += gridDim.x * 4) {
+        const int64_t row = (int64_t)n * ctx.tp + t;
+        const T *pa = ctx.fac_alpha(row), *pb = ctx.fac_beta(row);
+        const int *wa_ = ctx.fac_ea(row), *wb_ = ctx.fac_eb(row);
+        int cmax = INT_MIN;
+        for (int b = lane; b < nblk; b += 32) {
+            int ea, eb, da, db;
+            T fa, fb;
+            fac_unpack_norm<T>(wa_[b], ea, da, fa);
+            fac_unpack_norm<T>(wb_[b], eb, db, fb);
+            T pm = T(0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pm = tmax(pm, (pa[b * 8 + j] * fa) * (pb[b * 8 + j] * fb));
+            if (pm > T(0)) cmax = max(cmax, ea + eb + Num<T>::pexp(pm));
+        }
+        cmax = __reduce_max_sync(ASG_FULL_MASK, cmax);
+        if (cmax == INT_MIN) continue;
+        for (int b = lane; b < nblk; b += 32) {
+            const int wa = wa_[b], wb = wb_[b];
+            if (!fac_live(wa) || !fac_live(wb)) continue;
+            int ea, eb, da, db;
+            T fa, fb;
+            fac_unpack_norm<T>(wa, ea, da, fa);
+            fac_unpack_norm<T>(wb, eb, db, fb);
+            const int c = ea + eb;
+            if (cmax - c >= Num<T>::kSafeGap + max(max(da, db), 0)) continue;        // coarse test clears almost every block
+            T al[8], be[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { al[j] = pa[b * 8 + j]; be[j] = pb[b * 8 + j]; }
+            risk |= fac_block_at_risk<T>(al, be, fa, fb, da, db, c, cmax);
+        }
+    }
+    if (__any_sync(ASG_FULL_MASK, risk) && lane == 0) atomicOr(out + n, RF_POSTERIOR_THIN);
+}
+
 extern "C" {
 
 int asg_layout(int dtype, int64_t T, int64_t N, int64_t L, int64_t S, asg_layout_t *out) {
@@ -343,6 +393,24 @@ int asg_logits_backward_fix(int dtype, const void *z, int64_t z_st, int64_t z_sn
                                                                     g_stride, scale, il, (int)T, (int)N, (int)L, (double *)grad_x);
     }
     return cuda_fail((int)cudaGetLastError(), "asg_logits_backward_fix");
+}
+
+int asg_range_flags(int dtype, const void *state, const void *ctx, int64_t T, int64_t N, int64_t L, int64_t S, int32_t *flags,
+                    asg_stream_t stream) {
+    asg_layout_t lay;
+    int rc = asg_layout(dtype, T, N, L, S, &lay);
+    if (rc) return rc;
+    if (!ctx || !flags) return fail(ASG_E_NULL, "asg_range_flags: ctx and flags are required");
+    const double *sc = reinterpret_cast<const double *>(static_cast<const char *>(ctx) + lay.off_scalars);
+    range_flags_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sc, (int)N, flags);
+    if (state) {
+        const dim3 grid((unsigned)std::min<int64_t>((T + 3) / 4, 64), (unsigned)N);
+        if (dtype == ASG_F32)
+            range_check_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(make_ctx<float>(const_cast<void *>(state), const_cast<void *>(ctx), lay, N), (int)N, flags);
+        else
+            range_check_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(make_ctx<double>(const_cast<void *>(state), const_cast<void *>(ctx), lay, N), (int)N, flags);
+    }
+    return cuda_fail((int)cudaGetLastError(), "asg_range_flags");
 }
 
 size_t asg_viterbi_scratch_bytes(int64_t T, int64_t N, int64_t S) {

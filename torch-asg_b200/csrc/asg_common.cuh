@@ -27,6 +27,14 @@ template <> struct Num<float> {
         k = max(-126, min(127, k));
         return __int_as_float((k + 127) << 23);
     }
+    // 2^k, exactly zero for k below the normal range (mass that far below is flushed, never clamped to the smallest normal)
+    __device__ __forceinline__ static float exp2i_flush(int k) { return k < -126 ? 0.0f : __int_as_float((min(k, 127) + 127) << 23); }
+    // Range report of the gradient assembly: a block b whose alpha and beta are both non-empty may hold entries flushed below
+    // 2^-126 of its maxima, i.e. lost products up to 2^(c_b - 121); the frame's largest product is 2^(cmax_eff - 237).  The loss is
+    // below 2^-24 of it iff cmax_eff - c_b >= kSafeGap.
+    static constexpr int kSafeGap = 127 + 110 - 126 + 5 + 24;      // = 140 (coarse test; fac_block_at_risk() is the per-position one)
+    static constexpr int kMantBits = 24;
+    __device__ __forceinline__ static float min_normal() { return 1.17549435e-38f; }
     // Posterior weights of the gradient assembly.  A block's products alpha_j * beta_j * prod_scale live in units of
     // 2^(ea + eb); pexp() is the biased exponent of the block's largest product, so ea + eb + pexp ranks the blocks of a
     // frame by their TRUE largest product (the mantissas are not normalised to [1,2): the scans renormalise lazily, and
@@ -75,6 +83,10 @@ template <> struct Num<double> {
         k = max(-1022, min(1023, k));
         return __hiloint2double((k + 1023) << 20, 0);
     }
+    __device__ __forceinline__ static double exp2i_flush(int k) { return k < -1022 ? 0.0 : __hiloint2double((min(k, 1023) + 1023) << 20, 0); }
+    static constexpr int kMantBits = 53;
+    __device__ __forceinline__ static double min_normal() { return 2.2250738585072014e-308; }
+    static constexpr int kSafeGap = 1023 + 960 - 1022 + 5 + 53;    // same argument: bias + product scale - min exponent + 5 + 53-bit margin
     __device__ __forceinline__ static int pexp(double pm) { return (__double2hiint(pm) >> 20) & 0x7ff; }
     __device__ __forceinline__ static int block_shift(int c, int cmax_eff) { return max(c - cmax_eff, -100000) + (1023 + 900); }
     static constexpr int kPostLog2 = 62;
@@ -112,10 +124,48 @@ template <> __device__ __forceinline__ double tmax<double>(double a, double b) {
 // m_j * 2^(E + d); d = -floor(log2 max_j m_j), so m_j * 2^d has its block maximum in [1,2) and E is the exponent of that
 // normalised block.  The fp32 scans renormalise lazily (their stored mantissas drift inside [2^-40, 8)) and record the
 // drift d so that the gradient assembly still multiplies NORMALISED mantissas (full fp32 range for the in-block spread);
-// consumers that normalise on every frame store d = 0.
+// consumers that normalise on every frame store d = 0.  An EMPTY block (all mantissas zero) stores d = -8, i.e. a zero low byte.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int fac_pack(int E_raw, int d) { return ((E_raw - d) << 8) | ((d + 8) & 0xff); }
+__device__ __forceinline__ int fac_pack(int E_raw, int d, bool live) { return live ? (((E_raw - d) << 8) | ((d + 8) & 0xff)) : (E_raw << 8); }
 __device__ __forceinline__ void fac_unpack(int w, int &E, int &d) { E = w >> 8; d = (w & 0xff) - 8; }
+__device__ __forceinline__ bool fac_live(int w) { return (w & 0xff) != 0; }
+// The drift field holds -8..247.  A generic (fp64) step whose block maximum fell by more than that stores NORMALISED mantissas
+// under the reserved code 247 = "drift up to 2^kFacDriftCoarseValue" (beyond that the scan itself raises the range flag).
+constexpr int kFacDriftCoarse = 247, kFacDriftCoarseValue = 900;
+__device__ __forceinline__ int fac_pack_coarse(int E_norm) { return ((E_norm - kFacDriftCoarse) << 8) | 0xff; }
+// For the gradient assembly: E = exponent of the block's NORMALISED mantissas, f = the factor that normalises the stored
+// ones times half of the product scale.  A drift so large that the factor would leave the format (a block whose maximum fell
+// by more than 2^72 in one frame) is normalised as far as representable and the rest stays in E.
+template <typename T> __device__ __forceinline__ void fac_unpack_norm(int w, int &E, int &d, T &f) {
+    fac_unpack(w, E, d);
+    if (sizeof(T) == 8 && d == kFacDriftCoarse) {       // fp64 only: normalised mantissas, "the maximum fell by up to 2^900"
+        E += d;
+        f = Num<T>::exp2i(Num<T>::kHalfProd);
+        d = kFacDriftCoarseValue;
+        return;
+    }
+    const int dc = min(d, Num<T>::kMaxShift + 1 - Num<T>::kHalfProd);
+    E += d - dc;
+    f = Num<T>::exp2i(dc + Num<T>::kHalfProd);
+}
+// Range report, per position (asg_range_flags, run on demand over the stored states; not on the step's path).  An entry of a
+// block that is zero (below the normal range) may be a FLUSHED one: up to 2^(-kMaxShift + drift) of its block maximum.  Paired
+// with the other factor AT THE SAME POSITION that bounds the product that may have been lost; the block is at risk when that bound
+// is not 2^-(mantissa bits) below the frame's largest product (ce units: exponent sum + biased exponent of the scaled product).
+template <typename T>
+__device__ __forceinline__ bool fac_block_at_risk(const T (&al)[8], const T (&be)[8], T fa, T fb, int da, int db, int c, int cmax) {
+    T a0 = T(0), b0 = T(0);          // largest normalised alpha where beta is zero, beta where alpha is zero
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (!(al[j] >= Num<T>::min_normal())) b0 = tmax(b0, be[j] * fb);
+        if (!(be[j] >= Num<T>::min_normal())) a0 = tmax(a0, al[j] * fa);
+    }
+    const int k = Num<T>::kHalfProd - Num<T>::kMaxShift + 3 + Num<T>::kMantBits;
+    bool risk = false;
+    if (b0 > T(0)) risk |= cmax - c < Num<T>::pexp(b0) + k + max(da, 0);
+    if (a0 > T(0)) risk |= cmax - c < Num<T>::pexp(a0) + k + max(db, 0);
+    return risk;
+}
 
 // ---------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) -- element-granular so arbitrary (element-aligned) strides are accepted

@@ -425,12 +425,14 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
             if (FAC) {
                 T av[2][8];
                 int ea[2], eb[2], da[2], db[2];
+                T fa[2], fb[2];                             // normalising factors of the stored mantissas (x half the product scale)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     lds8sw((const T *)(rowp[u] + offA), sw, av[u]);
                     lds8sw((const T *)(rowp[u] + offB), sw, bv[u]);
-                    fac_unpack(*(const int *)(rowp[u] + offEa), ea[u], da[u]);
-                    fac_unpack(*(const int *)(rowp[u] + offEb), eb[u], db[u]);
+                    const int wa = *(const int *)(rowp[u] + offEa), wb = *(const int *)(rowp[u] + offEb);
+                    fac_unpack_norm<T>(wa, ea[u], da[u], fa[u]);
+                    fac_unpack_norm<T>(wb, eb[u], db[u], fb[u]);
                 }
                 T pv[2][8];
                 int ep[2];                                  // exponent of the RAW mantissas of frame t-1 (E + d)
@@ -446,9 +448,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     // normalised mantissas (block maximum in [1,2)), each carrying half of the product scale
-                    const T fa = Num<T>::exp2i(da[u] + Num<T>::kHalfProd), fb = Num<T>::exp2i(db[u] + Num<T>::kHalfProd);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bv[u][j] = (av[u][j] * fa) * (bv[u][j] * fb);
+                    for (int j = 0; j < 8; ++j) bv[u][j] = (av[u][j] * fa[u]) * (bv[u][j] * fb[u]);
                     const T pm = tmax(tmax(tmax(bv[u][0], bv[u][1]), tmax(bv[u][2], bv[u][3])), tmax(tmax(bv[u][4], bv[u][5]), tmax(bv[u][6], bv[u][7])));
                     ps[u] = ((bv[u][0] + bv[u][1]) + (bv[u][2] + bv[u][3])) + ((bv[u][4] + bv[u][5]) + (bv[u][6] + bv[u][7]));
                     c[u] = ea[u] + eb[u];
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 for (int u = 0; u < 2; ++u) {
                     T left = __shfl_up_sync(ASG_FULL_MASK, last8(pv[u], fl), 1);
                     const int el = __shfl_up_sync(ASG_FULL_MASK, ep[u], 1);
-                    left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep[u], Num<T>::kMaxShift - 8));
+                    left = (lane == 0) ? T(0) : left * Num<T>::exp2i_flush(min(el - ep[u], Num<T>::kMaxShift - 8));
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const T stay = hreg[j] * pv[u][j];
@@ -565,11 +566,12 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     lds8sw(A_(r) + lb8, sw, av);
                     lds8sw(B_(r) + lb8, sw, bv);
                     int ea, eb, da, db;
-                    fac_unpack(Ea_(r)[le], ea, da);
-                    fac_unpack(Eb_(r)[le], eb, db);
+                    const int wa = Ea_(r)[le], wb = Eb_(r)[le];
+                    T fa, fb;
+                    fac_unpack_norm<T>(wa, ea, da, fa);
+                    fac_unpack_norm<T>(wb, eb, db, fb);
                     // alpha and beta mantissas are normalised separately (block maxima in [1,2) after the drift correction), so
                     // where one peaks the other can be ~2^-100: the products carry a constant 2^110 (2^960) to stay normal numbers
-                    const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) bv[j] = (av[j] * fa) * (bv[j] * fb);
                     const T pm = tmax(tmax(tmax(bv[0], bv[1]), tmax(bv[2], bv[3])), tmax(tmax(bv[4], bv[5]), tmax(bv[6], bv[7])));
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         // the left neighbour's last value, expressed in this block's exponent (bounded so den stays finite)
                         T left = __shfl_up_sync(ASG_FULL_MASK, last8(pv, fl), 1);
                         const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
-                        left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep, Num<T>::kMaxShift - 8));
+                        left = (lane == 0) ? T(0) : left * Num<T>::exp2i_flush(min(el - ep, Num<T>::kMaxShift - 8));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const T stay = hreg[j] * pv[j];
@@ -614,9 +616,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         lds8(B_(r) + b * 8, bv);
                         T pm = T(0);
                         int ea, eb, da, db;
-                        fac_unpack(Ea_(r)[b], ea, da);
-                        fac_unpack(Eb_(r)[b], eb, db);
-                        const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
+                        T fa, fb;
+                        fac_unpack_norm<T>(Ea_(r)[b], ea, da, fa);
+                        fac_unpack_norm<T>(Eb_(r)[b], eb, db, fb);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) pm = tmax(pm, (av[j] * fa) * (bv[j] * fb));
                         if (pm > T(0)) cmax = max(cmax, ea + eb + Num<T>::pexp(pm));
@@ -628,9 +630,10 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         lds8(A_(r) + b * 8, av);
                         lds8(B_(r) + b * 8, bv);
                         int ea, eb, da, db;
-                        fac_unpack(Ea_(r)[b], ea, da);
-                        fac_unpack(Eb_(r)[b], eb, db);
-                        const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
+                        const int wa = Ea_(r)[b], wb = Eb_(r)[b];
+                        T fa, fb;
+                        fac_unpack_norm<T>(wa, ea, da, fa);
+                        fac_unpack_norm<T>(wb, eb, db, fb);
                         const int c = ea + eb;
                         T pm = T(0), ps = T(0);
 #pragma unroll
@@ -644,9 +647,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                         lds8(A_(r) + b * 8, av);
                         lds8(B_(r) + b * 8, bv);
                         int ea, eb, da, db;
-                        fac_unpack(Ea_(r)[b], ea, da);
-                        fac_unpack(Eb_(r)[b], eb, db);
-                        const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
+                        T fa, fb;
+                        fac_unpack_norm<T>(Ea_(r)[b], ea, da, fa);
+                        fac_unpack_norm<T>(Eb_(r)[b], eb, db, fb);
                         const int c = ea + eb;
                         T pm = T(0);
 #pragma unroll

@@ -7,6 +7,18 @@
 
 namespace asg {
 
+// per-utterance float64 bookkeeping slots in Ctx::scalars
+enum { SC_R = 0, SC_FULL_BETA = 1, SC_FULL_ALPHA = 2, SC_RB = 3, SC_AL_BETA = 4, SC_AL_ALPHA = 5,
+       SC_FCC_LOGSCALE_END = 6, SC_FLAGS = 7 };
+
+// Range flags of an utterance (an int32 in the SC_FLAGS slot; cleared by asg_scan, OR-ed by the kernels, read by asg_range_flags):
+// the real-domain / block-floating-point arithmetic covers ~87 nats (fp32; 708 in fp64) of dynamic range between the entries
+// that share a frame maximum or a block exponent; beyond that mass is flushed to zero (never clamped) and these bits say so.
+enum { RF_EMISSION_UNDERFLOW = 1,   // a finite emission lies more than the format's range below its frame's maximum: exp(x - max) = 0
+       RF_POSTERIOR_THIN = 2,       // in some frame a block of target positions could hold FLUSHED entries (more than 2^126 below the
+                                    // block's maxima) whose alpha*beta product is not negligible against the frame's largest one
+       RF_SCORE_LOST = 4 };         // the aligned score of a feasible utterance came out as -inf
+
 // typed view of the frame-record array + the context blob (see asg_layout_t)
 template <typename T> struct Ctx {
     char *rec;        // [N,tp] frame records
@@ -21,6 +33,7 @@ template <typename T> struct Ctx {
     int64_t *il;      // [N]
     int64_t *tl;      // [N]
     double *scalars;  // [N,8]
+    __host__ __device__ __forceinline__ int *flags(int64_t n) const { return reinterpret_cast<int *>(scalars + n * 8 + SC_FLAGS); }
     int64_t sp, nblk, nbp, lpi, tp;
     __host__ __device__ __forceinline__ char *record(int64_t row) const { return rec + row * R; }
     __host__ __device__ __forceinline__ T *fac_alpha(int64_t row) const { return (T *)(rec + row * R + o_fa); }
@@ -32,10 +45,6 @@ template <typename T> struct Ctx {
     __host__ __device__ __forceinline__ T *fcc_w(int64_t row) const { return (T *)(rec + row * R + o_cw); }
     __host__ __device__ __forceinline__ T *fcc_scale(int64_t row) const { return (T *)(rec + row * R + o_sc); }
 };
-
-// per-utterance float64 bookkeeping slots in Ctx::scalars
-enum { SC_R = 0, SC_FULL_BETA = 1, SC_FULL_ALPHA = 2, SC_RB = 3, SC_AL_BETA = 4, SC_AL_ALPHA = 5,
-       SC_FCC_LOGSCALE_END = 6, SC_SPARE = 7 };
 
 template <typename T> inline Ctx<T> make_ctx(void *state, void *blob, const asg_layout_t &lay, int64_t N) {
     char *b = static_cast<char *>(blob);

@@ -634,9 +634,10 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
 #pragma unroll
             for (int j = 0; j < 8; ++j) { av[j] = pa[j]; bv[j] = pb[j]; }
             int ea, eb, da, db;
-            fac_unpack(a.ctx.fac_ea(row)[be], ea, da);
-            fac_unpack(a.ctx.fac_eb(row)[be], eb, db);
-            const T fa = Num<T>::exp2i(da + Num<T>::kHalfProd), fb = Num<T>::exp2i(db + Num<T>::kHalfProd);
+            const int wa = a.ctx.fac_ea(row)[be], wb = a.ctx.fac_eb(row)[be];
+            T fa, fb;
+            fac_unpack_norm<T>(wa, ea, da, fa);
+            fac_unpack_norm<T>(wb, eb, db, fb);
             T pm = T(0), ps = T(0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * fa) * (bv[j] * fb); pm = tmax(pm, bv[j]); ps += bv[j]; }

@@ -94,6 +94,7 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
             cp_async_commit();
         }
         double msum = 0.0;
+        bool uflow = false;                                     // a finite emission underflowed against its frame's maximum
         int b = 0, g = 0;
         while (b < nb || g < ngroups) {
             const int c = consumed_min();
@@ -127,6 +128,9 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
                     if (valid && sub + 4 * i < V) {
                         float4 u;
                         u.x = expf(xv[i].x - m); u.y = expf(xv[i].y - m); u.z = expf(xv[i].z - m); u.w = expf(xv[i].w - m);
+                        const float ninf_ = Num<float>::neg_inf();
+                        uflow |= ((u.x == 0.f) & (xv[i].x > ninf_)) | ((u.y == 0.f) & (xv[i].y > ninf_)) | ((u.z == 0.f) & (xv[i].z > ninf_)) |
+                                 ((u.w == 0.f) & (xv[i].w > ninf_));
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 64u * i), "f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w) : "memory");
                     }
                 }
@@ -144,6 +148,7 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
                     cp_async_wait<0>();
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(ASG_FULL_MASK, msum, o);
+                    if (__any_sync(ASG_FULL_MASK, uflow) && lane == 0) atomicOr(a.ctx.flags(n), RF_EMISSION_UNDERFLOW);
                     if (lane == 0) {
                         *msum_out = msum;
                         __threadfence_block();
@@ -189,7 +194,12 @@ __device__ __forceinline__ void scan_producer(const ScanArgs<T> &a, T *raw, int 
             if (!(m > ninf)) m = T(0);                     // an all -inf frame
             T *dst = uring + (size_t)(k % RING) * up;
             if (valid)                                     // (slots of frames >= Tn belong to frames not yet consumed)
-                for (int l = sub; l < up; l += 4) dst[l] = (l < L && (!gather || glab[l] >= 0)) ? Num<T>::exp_(src[l] - m) : T(0);
+                for (int l = sub; l < up; l += 4) {
+                    const bool on = l < L && (!gather || glab[l] >= 0);
+                    const T uu = on ? Num<T>::exp_(src[l] - m) : T(0);
+                    if (on && uu == T(0) && src[l] > ninf) atomicOr(a.ctx.flags(n), RF_EMISSION_UNDERFLOW);     // rare
+                    dst[l] = uu;
+                }
             if (valid && sub == 0) msum += (double)m;
             if (b + NRAW < nb) issue(b + NRAW);            // each lane re-fills only elements it has consumed itself
             cp_async_commit();
@@ -756,7 +766,9 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
 
     T v[ASG_BLK];        // alpha: P ; beta: Q (mantissas)
     T w[ASG_BLK];        // beta only: emission-weighted state fed to the next step
-    int Eme = 0;
+    T sv[ASG_BLK];       // what is stored for the frame: the state before normalisation, in units of 2^sE, maximum ~2^-sdrift
+    int Eme = 0, sE = 0, sdrift = 0;
+    bool drop_seen = false, coarse = false;
     T mymax = T(0);      // max of what feeds the next step (alpha: v, beta: w)
     int cur = 0;
 
@@ -778,6 +790,7 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
             for (int j = 0; j < ASG_BLK; ++j) {
                 if (BETA) v[j] = (s0 + j == Sn - 1) ? T(1) : T(0);
                 else v[j] = (s0 + j == 0) ? ub[j] : T(0);
+                sv[j] = v[j];
             }
         } else {
             // neighbour's boundary value and exponent from the previous step
@@ -799,8 +812,8 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
             int Enew = Eme;
             if (mymax == T(0)) Enew = ne;
             else if (nv > T(0)) Enew = max(Eme, ne - KNB);
-            const T fs = Num<T>::exp2i(Eme - Enew);                // <= 1 (1 in the common case)
-            nv *= Num<T>::exp2i(ne - Enew);
+            const T fs = Num<T>::exp2i_flush(Eme - Enew);          // <= 1 (1 in the common case)
+            nv *= Num<T>::exp2i_flush(ne - Enew);                  // more than the format's range below: flushed to zero, never clamped
             Eme = Enew;
             T r[ASG_BLK];
             if (BETA) {
@@ -824,8 +837,20 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
             const T m = tmax(tmax(tmax(r[0], r[1]), tmax(r[2], r[3])), tmax(tmax(r[4], r[5]), tmax(r[6], r[7])));
             T sc; int e;
             Num<T>::pow2_norm(m, sc, e);
+            // What is STORED for this frame is the state before normalisation together with the drift of its maximum, so
+            // the gradient assembly knows how far below the block maximum entries may have been flushed in this step (range
+            // report).  A drift that does not fit the exponent word: stored normalised (fac_pack_coarse), a drop beyond 2^900 is reported here.
+            sdrift = -e;
+            sE = Eme;
+            const bool raw = sdrift < kFacDriftCoarse && sdrift >= -7;   // (a maximum above 2^7 is inflow from a far larger neighbour)
+            if (!raw) {
+                coarse = sdrift >= kFacDriftCoarse;                      // stored normalised under the reserved drift code
+                drop_seen |= sdrift > kFacDriftCoarseValue;
+                sdrift = 0;
+                sE = Eme + e;
+            } else coarse = false;
 #pragma unroll
-            for (int j = 0; j < ASG_BLK; ++j) v[j] = r[j] * sc;
+            for (int j = 0; j < ASG_BLK; ++j) { v[j] = r[j] * sc; sv[j] = raw ? r[j] : v[j]; }
             Eme += e;
         }
         // what feeds the next step, and its max
@@ -839,8 +864,8 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
 
         // store mantissas + exponent
         if (store) {
-            store8_stream(stp, v);
-            if (store_e) *esp = fac_pack(Eme, 0);
+            store8_stream(stp, sv);
+            if (store_e) *esp = coarse ? fac_pack_coarse(sE) : fac_pack(sE, sdrift, tmax(tmax(tmax(sv[0], sv[1]), tmax(sv[2], sv[3])), tmax(tmax(sv[4], sv[5]), tmax(sv[6], sv[7]))) > T(0));
         }
         stp += sstep;
         esp += estep;
@@ -852,6 +877,7 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
         }
     }
     if (lane == 0) st_volatile_s32(&sm.consumed[warp], Tn);
+    if (__any_sync(ASG_FULL_MASK, drop_seen) && lane == 0) atomicOr(a.ctx.flags(n), RF_POSTERIOR_THIN);
     // ---- score ------------------------------------------------------------------------------------
     const double msum = (Tn > 0) ? wait_msum(sm.msum, &sm.flags[1]) : 0.0;
     if (gl == 0) {
@@ -860,6 +886,7 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
             // beta: w[0] = u_0[y_0] * Q_0[0];  alpha: total mass in the final position S_n-1 is read below
             const T fin = BETA ? w[0] : T(0);
             score = (double)Num<T>::log_(fin) + msum + (double)(Tn - 1) * (double)Rb + (double)Eme * 0.6931471805599453094;
+            if (BETA && !(fin > T(0)) && Sn <= Tn) atomicOr(a.ctx.flags(n), RF_SCORE_LOST);
         }
         if (BETA) {
             a.ctx.scalars[(int64_t)n * 8 + SC_AL_BETA] = score;
@@ -1020,7 +1047,7 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
         fix = __any_sync(ASG_FULL_MASK, flag);
         stg_cs_v4_if(sptr, St[0].x, St[1].x, St[2].x, St[3].x, store);
         stg_cs_v4_if(sptr + 16, St[0].y, St[1].y, St[2].y, St[3].y, store);
-        stg_s32_if(eptr, fac_pack(Eme, live ? 127 - (int)me : 0), store_e);     // E and the drift of the block maximum
+        stg_s32_if(eptr, fac_pack(Eme, 127 - (int)me, live), store_e);          // E, the drift of the block maximum, live / empty
         sptr += rstep;
         eptr += rstep;
     };
@@ -1097,6 +1124,7 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
         if (Tn > 0) {
             const T fin = BETA ? Wf[0].x : T(0);
             score = (double)Num<T>::log_(fin) + msum + (double)(Tn - 1) * (double)Rb + (double)Eme * 0.6931471805599453094;
+            if (BETA && !(fin > T(0)) && Sn <= Tn) atomicOr(a.ctx.flags(n), RF_SCORE_LOST);
         }
         if (BETA) {
             a.ctx.scalars[(int64_t)n * 8 + SC_AL_BETA] = score;
@@ -1390,6 +1418,8 @@ template <typename T> int launch_scan(const ScanArgs<T> &a_in, int roles, cudaSt
         int rc = large_prepare<T>(a_in, stream);
         if (rc) return rc;
     }
+    // range flags of this call start clear (the scalars block is rewritten by every scan anyway)
+    if ((e = cudaMemsetAsync(a_in.ctx.scalars, 0, sizeof(double) * 8 * (size_t)a_in.d.N, stream)) != cudaSuccess) return (int)e;
     cudaStream_t side = nullptr;
     SideSlot slot{};
     if (any_fcc && any_fac && side_slot(device, stream, slot)) {

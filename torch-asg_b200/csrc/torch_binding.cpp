@@ -241,6 +241,21 @@ std::tuple<Tensor, Tensor> fast_asg_gpu_backward(Tensor &grad_full, Tensor &grad
     return {grad_A, grad_x};
 }
 
+// not in the reference: the range report of a context blob (asg_range_flags): int32 [N]
+Tensor range_flags(Tensor &state, Tensor &ctx, bool is_double, int64_t T, int64_t N, int64_t L, int64_t S) {
+    check_cuda(ctx, "ctx");
+    check_cuda(state, "state");
+    const asg_layout_t lay = layout_of(is_double ? ASG_F64 : ASG_F32, T, N, L, S);
+    TORCH_CHECK((size_t)ctx.numel() == lay.ctx_bytes && ctx.scalar_type() == at::kByte, "not a context blob for these dimensions");
+    // forward_only results carry no states (an empty tensor): only the flags the scans raise themselves are reported then
+    const bool has_state = (size_t)state.numel() == lay.state_bytes && state.scalar_type() == at::kByte;
+    TORCH_CHECK(has_state || state.numel() == 0, "not a state array for these dimensions");
+    c10::cuda::CUDAGuard guard(ctx.device());
+    Tensor out = at::empty({N}, ctx.options().dtype(at::kInt));
+    check_rc(asg_range_flags(is_double ? ASG_F64 : ASG_F32, has_state ? state.data_ptr() : nullptr, ctx.data_ptr(), T, N, L, S, out.data_ptr<int32_t>(), current_stream()));
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Workspace: every buffer one (dtype, T, N, L, S) problem needs, allocated ONCE, so a step is pure kernel launches
 // (asg_forward / asg_backward / asg_step allocate nothing and never synchronise) and can be captured in a CUDA graph.
@@ -299,6 +314,7 @@ struct Workspace {
                               ctx.data_ptr(), y.data_ptr<int64_t>(), y.stride(0), y.stride(1), T, N, L, S, grad_x.data_ptr(),
                               fused.data_ptr(), scratch.data_ptr(), current_stream()));
     }
+    Tensor flags() { return range_flags(state, ctx, dt == ASG_F64, T, N, L, S); }
     void step(Tensor &x, Tensor &A, Tensor &y, Tensor &il, Tensor &tl, double scale) {
         check(x, A, y, il, tl);
         c10::cuda::CUDAGuard guard(x.device());
@@ -372,6 +388,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def("forward", &Workspace::forward)
         .def("backward", &Workspace::backward)
         .def("step", &Workspace::step)
+        .def("range_flags", &Workspace::flags)
         .def_readonly("full_scores", &Workspace::full)
         .def_readonly("aligned_scores", &Workspace::aligned)
         .def_readonly("losses", &Workspace::losses)
@@ -382,6 +399,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def_readonly("state", &Workspace::state)
         .def_readonly("ctx", &Workspace::ctx)
         .def_readonly("T", &Workspace::T).def_readonly("N", &Workspace::N).def_readonly("L", &Workspace::L).def_readonly("S", &Workspace::S);
+    m.def("range_flags", &range_flags, "per-utterance range report of (state, ctx) (asg_range_flags), int32 [N] (not in the reference)");
     m.def("viterbi_align", &viterbi_align, "Viterbi forced alignment: (scores[N], path[N,T]) (not in the reference)");
     m.def("logits_backward_fix", &logits_backward_fix,
           "fused log_softmax + ASG: in-place correction of grad_x for infeasible utterances (not in the reference)");

@@ -300,6 +300,12 @@ class GraphedASGLoss(nn.Module):
         return e.gloss
 
     @property
+    def range_flags(self):
+        """int32 [N] range report of the most recent call (``asg_range_flags``): 0 everywhere unless the inputs are so peaked
+        that fp32's ~87 nats of in-frame / in-block dynamic range were exceeded; rerun such a batch in float64."""
+        return next(reversed(self._entries.values())).ws.range_flags()
+
+    @property
     def global_loss(self):
         """After a backward (or step): the reduced loss over ALL ranks' utterances, from the all-reduced fused buffer."""
         ws = next(reversed(self._entries.values())).ws
