@@ -296,7 +296,7 @@ def run_b200(args):
     # The public surface with the workspace + CUDA graphs behind it (torch_asg/graphed.py).  Batch-sharded runs pass the
     # process group: the backward graph then ends with the one fused all-reduce [L*L+2].
     gcrit = torch_asg.GraphedASGLoss(crit, group=(dist.group.WORLD if world > 1 else None), global_batch=N * world,
-                                     use_graph=(args.api != "eager-ws"), max_graphs=4 * nsets)
+                                     use_graph=(args.api != "eager-ws"), max_graphs=4 * nsets, exchange=args.exchange)
     last = {}
 
     # Every step hands its input gradient to `last` (what an acoustic model's backward would consume) and clears
@@ -498,8 +498,9 @@ def run_b200(args):
         "config": {"workload": "%s: T=%d N=%d per GPU (global %d) L=%d S=%d, ASGLoss(mean) %s, full lengths"
                                % (args.workload, T, N, N * world, L, S, "forward-only" if fwd_only else "fwd+bwd"),
                    "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); no flush" % (nsets, nsets * per_set / 1e6),
-                   "parallelism": "batch-sharded, one fused all-reduce [L*L+2] (NCCL%s)" % (
-                       ", captured in the backward graph" if gcrit.nccl_in_graph else ", eager") if world > 1 else "single GPU",
+                   "parallelism": ("batch-sharded, one exchange per step: sum over ranks of the fused vector [L*L+2], " + (
+                       "one peer-memory kernel per rank over NVLink (asg_peer_allreduce), inside the step's graph" if gcrit.exchange == "peer"
+                       else "NCCL all-reduce%s" % (", captured in the graph" if gcrit.nccl_in_graph else ", eager"))) if world > 1 else "single GPU",
                    "api": "ASGLoss forward under no_grad (forward-only graph)" if fwd_only else api_text,
                    "graph_replays": replays, "loss": loss_val, "other_routes": side},
         "gpu_launches": launches, "kernels": kernels, "clocks": clocks,
@@ -656,6 +657,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how the fused [L*L+2] vector is summed over ranks (auto = the peer-memory kernel when the GPUs have peer access)")
     ap.add_argument("--api", default="step", choices=["graph", "step", "eager-ws", "eager"],
                     help="timed loop: step = GraphedASGLoss.step (default): the graph behind ASGLoss + backward() -- forward, backward and the "
                          "all-reduce as one replay, gradients delivered to inputs.grad / transition.grad; graph = GraphedASGLoss(...)(...) + "

@@ -285,6 +285,33 @@ int asg_host_submit(asg_host_ctx_t *h,
                     void *loss, void *grad_x, void *grad_A);
 int asg_host_wait(asg_host_ctx_t *h);
 
+/*
+ * The exchange step of a batch-sharded job (one process per GPU, utterances sharded over ranks): the sum over ranks
+ * of the fused vector [L*L transition gradient | loss sum | utterance count] that asg_backward / asg_step leave in `fused`.
+ * The reference has no multi-GPU path of its own (its users wrap the criterion in DistributedDataParallel, which all-reduces
+ * transition.grad through NCCL); this is that exchange written over NVLink peer memory, as ONE kernel per rank per step:
+ * every rank stores its vector into every rank's exchange buffer, raises a flag there, waits for all flags to arrive locally
+ * and adds the slots in rank order (bit-identical result on every rank).  No library collective, no host involvement, no
+ * per-call argument: it replays inside a CUDA graph.
+ *
+ *   asg_peer_create   allocates this rank's exchange buffer (cudaMalloc on the current device) and returns its CUDA IPC handle
+ *                     (ASG_PEER_HANDLE_BYTES bytes) for the caller to all-gather over whatever channel it has;
+ *   asg_peer_connect  opens the other ranks' buffers (handles: world * ASG_PEER_HANDLE_BYTES bytes in rank order); fails with
+ *                     a message when a peer is not reachable by peer access -- the caller then keeps its library collective;
+ *   asg_peer_allreduce  in-place sum of buf[count] (dtype) over all ranks, stream-ordered; count * sizeof <= max_bytes;
+ *                     every rank must issue the same sequence of calls;
+ *   asg_peer_status   (synchronising) the number of exchanges done and the epoch of the first one that timed out waiting
+ *                     for a peer (0 = none; a rank gives up after 4 s instead of hanging the GPU and leaves buf untouched).
+ * world <= 8 (one NVSwitch domain).
+ */
+#define ASG_PEER_HANDLE_BYTES 64
+typedef struct asg_peer asg_peer_t;
+int asg_peer_create(int rank, int world, size_t max_bytes, asg_peer_t **out, void *handle);
+int asg_peer_connect(asg_peer_t *p, const void *handles);
+int asg_peer_allreduce(asg_peer_t *p, int dtype, void *buf, int64_t count, asg_stream_t stream);
+int asg_peer_status(asg_peer_t *p, uint64_t *epoch, uint64_t *timed_out_epoch);
+int asg_peer_destroy(asg_peer_t *p);
+
 /* Destroys the side streams and events the library created for asg_scan()'s FCC/FAC overlap (one set per
  * (device, caller stream) pair).  Optional; call when no work of this library is in flight. */
 void asg_release(void);

@@ -67,14 +67,14 @@ static void prof_drain() {
     g_prof_recs.clear();
 }
 
-static int fail(int code, const char *fmt, ...) {
+int fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
-static int cuda_fail(int e, const char *where) {
+int cuda_fail(int e, const char *where) {
     if (e == 0) return 0;
     return fail(e, "%s: CUDA error %d (%s)", where, e, cudaGetErrorString((cudaError_t)e));
 }
@@ -604,7 +604,7 @@ int asg_profile_read(int kernel_id, double *total_ms, uint64_t *launches) {
     return 0;
 }
 const char *asg_kernel_name(int kernel_id) {
-    static const char *names[K_COUNT] = {"fcc_scan_kernel", "fac_scan_kernel", "grad_kernel", "grad_finalize_kernel", "host_misc", "grad_large_gemm_kernel"};
+    static const char *names[K_COUNT] = {"fcc_scan_kernel", "fac_scan_kernel", "grad_kernel", "grad_finalize_kernel", "host_misc", "grad_large_gemm_kernel", "peer_allreduce_kernel"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : "";
 }
 int asg_kernel_count(void) { return K_COUNT; }

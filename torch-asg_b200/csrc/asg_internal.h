@@ -123,6 +123,8 @@ int grad_grid_size(int device);   // number of persistent CTAs asg_grad launches
 int large_splitk_host(int L);
 size_t large_ws_bytes(size_t elem_bytes, int64_t N, int64_t L);   // asg_large.cu     // K splits of the large-alphabet transition-gradient contraction (asg_large.cu)
 void count_launch(int n = 1);
+int fail(int code, const char *fmt, ...);            // records asg_last_error(), returns code
+int cuda_fail(int e, const char *where);             // 0 stays 0
 void release_side_slots();          // asg_scan.cu: asg_release()
 // asg_viterbi.cu
 int viterbi_words(int64_t S);
@@ -131,7 +133,7 @@ int viterbi_dispatch(int dtype, const void *x, int64_t x_st, int64_t x_sn, int64
                      int64_t S, void *scores, int64_t *path, void *scratch, cudaStream_t st);
 
 // kernel ids for the launch counter / live profiler (asg_profile_* in include/asg_b200.h)
-enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_GRAD_GEMM = 5, K_COUNT = 6 };
+enum { K_FCC_SCAN = 0, K_FAC_SCAN = 1, K_GRAD = 2, K_GRAD_FINALIZE = 3, K_HOST_MISC = 4, K_GRAD_GEMM = 5, K_PEER_ALLREDUCE = 6, K_COUNT = 7 };
 
 // RAII: counts one launch of kernel `kid` and, while profiling is enabled, brackets it with a pair
 // of CUDA events recorded on the launching stream (read back by asg_profile_read()).

@@ -325,6 +325,39 @@ struct Workspace {
     }
 };
 
+// not in the reference: the exchange step of a batch-sharded job over NVLink peer memory (asg_peer_*)
+struct PeerComm {
+    asg_peer_t *p = nullptr;
+    int64_t device;
+    std::string handle_;
+    PeerComm(int64_t rank, int64_t world, int64_t max_bytes, int64_t device_) : device(device_) {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+        char h[ASG_PEER_HANDLE_BYTES];
+        check_rc(asg_peer_create((int)rank, (int)world, (size_t)max_bytes, &p, h));
+        handle_.assign(h, sizeof(h));
+    }
+    ~PeerComm() { if (p) { c10::cuda::CUDAGuard guard((c10::DeviceIndex)device); asg_peer_destroy(p); } }
+    PeerComm(const PeerComm &) = delete;
+    pybind11::bytes handle() const { return pybind11::bytes(handle_); }
+    void connect(const std::string &handles) {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+        check_rc(asg_peer_connect(p, handles.data()));
+    }
+    void allreduce(Tensor &buf) {
+        check_cuda(buf, "buf");
+        TORCH_CHECK(buf.is_contiguous() && (buf.scalar_type() == at::kFloat || buf.scalar_type() == at::kDouble) && buf.get_device() == device,
+                    "peer all-reduce takes a contiguous float32/float64 tensor on the communicator's device");
+        c10::cuda::CUDAGuard guard(buf.device());
+        check_rc(asg_peer_allreduce(p, buf.scalar_type() == at::kDouble ? ASG_F64 : ASG_F32, buf.data_ptr(), buf.numel(), current_stream()));
+    }
+    std::pair<uint64_t, uint64_t> status() {
+        c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+        uint64_t e = 0, t = 0;
+        check_rc(asg_peer_status(p, &e, &t));
+        return {e, t};
+    }
+};
+
 // not in the reference: the backward correction of the fused log_softmax + ASG path (asg_logits_backward_fix)
 void logits_backward_fix(Tensor &z, Tensor &aligned, Tensor &g, double scale, Tensor &input_lengths, Tensor &grad_x) {
     check_cuda(z, "inputs");
@@ -399,6 +432,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def_readonly("state", &Workspace::state)
         .def_readonly("ctx", &Workspace::ctx)
         .def_readonly("T", &Workspace::T).def_readonly("N", &Workspace::N).def_readonly("L", &Workspace::L).def_readonly("S", &Workspace::S);
+    pybind11::class_<PeerComm>(m, "PeerComm", "exchange buffers of a batch-sharded job over NVLink peer memory (asg_peer_*)")
+        .def(pybind11::init<int64_t, int64_t, int64_t, int64_t>(), pybind11::arg("rank"), pybind11::arg("world"), pybind11::arg("max_bytes"),
+             pybind11::arg("device"))
+        .def("handle", &PeerComm::handle)
+        .def("connect", &PeerComm::connect)
+        .def("allreduce", &PeerComm::allreduce)
+        .def("status", &PeerComm::status);
     m.def("range_flags", &range_flags, "per-utterance range report of (state, ctx) (asg_range_flags), int32 [N] (not in the reference)");
     m.def("viterbi_align", &viterbi_align, "Viterbi forced alignment: (scores[N], path[N,T]) (not in the reference)");
     m.def("logits_backward_fix", &logits_backward_fix,

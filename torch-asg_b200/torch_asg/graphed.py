@@ -15,13 +15,16 @@ the call capturable.  Graphs are keyed by the addresses they were captured with 
 transition); a new address captures a new graph (a small LRU), ``use_graph=False`` runs the same zero-allocation
 calls eagerly.
 
-Batch-sharded jobs: pass ``group``; the backward graph then ends with the ONE all-reduce of the fused
-``[L*L + 2]`` buffer (transition gradient, loss sum, utterance count) -- NCCL, captured in the graph -- so
-``transition.grad`` is the global gradient on every rank and ``global_loss`` the global reduced loss.  The value
-``forward`` returns is this rank's share of the reduced loss (its sum over ranks is the global loss).
-Set ``NCCL_GRAPH_MIXING_SUPPORT=0`` before ``init_process_group`` when all collectives of the job are issued in program
-order from one thread (true for this module): with NCCL's default, every launch of a graph that holds a collective waits
-on the host for the previous one (measured on 2 x B200: 0.10-0.25 ms per replay instead of 0.005 ms).
+Batch-sharded jobs: pass ``group``; the backward graph then ends with the ONE exchange of the job, the sum
+over ranks of the fused ``[L*L + 2]`` buffer (transition gradient, loss sum, utterance count), so ``transition.grad`` is
+the global gradient on every rank and ``global_loss`` the global reduced loss.  The value ``forward`` returns is this
+rank's share of the reduced loss (its sum over ranks is the global loss).  ``exchange``:
+  'peer'  one kernel of this library per rank over NVLink peer memory (torch_asg/peer.py, C ABI ``asg_peer_*``): no
+          library collective in the graph, the replay costs the host what a single-GPU replay costs;
+  'nccl'  ``dist.all_reduce`` captured in the graph.  Set ``NCCL_GRAPH_MIXING_SUPPORT=0`` before ``init_process_group``
+          then: with NCCL's default every launch of a graph that holds a collective waits on the host for the previous
+          one (measured on 2 x B200: 0.10-0.25 ms per replay);
+  'auto'  (default) 'peer' when all ranks sit on one host with peer access between every pair of GPUs, else 'nccl'.
 
 Reference semantics kept: ``reduction`` 'mean' / 'sum' / anything else = none (asg.py:137-142), default lengths
 (asg.py:113-117), ``forward_only`` / eval = the two beta scans only and no gradient (asg.py:129-131).
@@ -79,10 +82,15 @@ class _GraphedFn(torch.autograd.Function):
 
 
 class GraphedASGLoss(nn.Module):
-    def __init__(self, criterion, group=None, global_batch=None, use_graph=True, max_graphs=32):
+    def __init__(self, criterion, group=None, global_batch=None, use_graph=True, max_graphs=32, exchange="auto"):
         super().__init__()
         self.criterion = criterion
         self.group = group
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self.exchange = exchange            # how the fused vector is summed over ranks; resolved on first use (collective)
+        self._peer = None
+        self._exchange_resolved = False
         self.global_batch = global_batch
         self.use_graph = use_graph
         self.max_graphs = max_graphs
@@ -144,6 +152,7 @@ class GraphedASGLoss(nn.Module):
         T, N, L = inputs.shape
         S = targets.shape[1]
         A = self.criterion.transition
+        self._resolve_exchange(inputs.device)
         wkey = (inputs.dtype, inputs.device, T, N, L, S)
         ws = self._ws.get(wkey)
         if ws is None:
@@ -169,11 +178,36 @@ class GraphedASGLoss(nn.Module):
             self._entries.move_to_end(key)
         return e
 
-    def _tail_and_reduce(self, ws):
-        """fused = grad_A | loss sum | count, then the one collective of a batch-sharded job."""
-        ws.fused[-2:].copy_(ws.loss_tail[:2])
+    def _resolve_exchange(self, device):
+        """'auto' -> the peer-memory kernel (torch_asg/peer.py) when every pair of ranks has peer access, else NCCL.
+        Collective; runs once, outside any capture."""
+        if self._exchange_resolved:
+            return
+        self._exchange_resolved = True
+        if self.exchange in ("peer", "auto") and self._peer is None and _world(self.group) > 1:
+            from .peer import PeerAllReduce
+            self._peer = PeerAllReduce.create(self._native, self.group, device)
+            if self._peer is None:
+                if self.exchange == "peer":
+                    raise RuntimeError("GraphedASGLoss(exchange='peer'): the ranks have no peer access to each other")
+                self.exchange = "nccl"
+            else:
+                self.exchange = "peer"
+        elif self.exchange == "auto":
+            self.exchange = "nccl"
+
+    def _exchange(self, ws):
+        """The one exchange of a batch-sharded job: fused <- sum over ranks."""
         if _world(self.group) > 1:
-            dist.all_reduce(ws.fused, op=dist.ReduceOp.SUM, group=self.group)
+            if self._peer is not None:
+                self._peer.all_reduce(ws.fused)
+            else:
+                dist.all_reduce(ws.fused, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _tail_and_reduce(self, ws):
+        """fused = grad_A | loss sum | count, then the one exchange of a batch-sharded job."""
+        ws.fused[-2:].copy_(ws.loss_tail[:2])
+        self._exchange(ws)
 
     def _body(self, e, kind, args):
         ws = e.ws
@@ -188,8 +222,7 @@ class GraphedASGLoss(nn.Module):
             self._tail_and_reduce(ws)
         else:                               # "step": the whole training step
             ws.step(x, A, y, il, tl, scale)
-            if _world(self.group) > 1:
-                dist.all_reduce(ws.fused, op=dist.ReduceOp.SUM, group=self.group)
+            self._exchange(ws)
             if e.gloss is None:
                 e.gloss = torch.zeros((), dtype=ws.fused.dtype, device=ws.fused.device)
             if self.criterion.reduction == 'mean':
@@ -246,7 +279,7 @@ class GraphedASGLoss(nn.Module):
                 self.nccl_in_graph = False
             return False
         if _world(self.group) > 1 and kind in ("bwd", "step"):
-            self.nccl_in_graph = True
+            self.nccl_in_graph = self._peer is None
         g.replay()                          # the first launch of an instantiated graph uploads it to the device: pay that here
         return g
 
