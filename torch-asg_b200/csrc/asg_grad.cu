@@ -88,11 +88,19 @@ template <> struct Pk<double> {
 };
 
 // approximate (float) / exact (double) quotient for the edge posteriors
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
-// correctly rounded reciprocal without the division's range checks (float), exact division (double)
-__device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
+// float: ONE MUFU.RCP (1 ulp; __fdividef adds a range-scaling sequence and __frcp_rn a refinement with a slow-path branch, both
+// of which the callers' operand ranges make unnecessary: every divisor is floored at Num::tiny() and no quotient exceeds 2^100)
+__device__ __forceinline__ float rcp_(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fast_div(float a, float b) { return a * rcp_(b); }
+__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
+// posterior bins of the fast path: a shared-memory reduction at a precomputed 32-bit address (no return value, no per-element
+// address arithmetic); float only -- the double bins are 64-bit (add64_shared)
+__device__ __forceinline__ void red_shared_s32(unsigned addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // shared-memory map: [per-CTA block][stage 0][stage 1]...   A stage holds TB+1 frame records (the halo record of
 // frame t0-1 first) exactly as they lie in global memory, plus the tile's winv scalars.
@@ -156,6 +164,40 @@ __device__ __forceinline__ void lds8sw(const double *p, int sw, double (&v)[8]) 
         const double2 b = *(reinterpret_cast<const double2 *>(p + (4 - sw)) + q);
         v[2 * q] = a.x; v[2 * q + 1] = a.y; v[4 + 2 * q] = b.x; v[4 + 2 * q + 1] = b.y;
     }
+}
+// The same loads by 32-bit shared address (fast path: one integer add per load instead of 64-bit generic-pointer arithmetic).
+// a_lo / a_hi: the addresses of the block's two 16-byte halves, already swapped for permuted lanes.
+__device__ __forceinline__ void lds8_at(unsigned a_lo, unsigned a_hi, float (&v)[8]) {
+    const float4 a = lds_v4f32(a_lo), b = lds_v4f32(a_hi);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8_at(unsigned a_lo, unsigned a_hi, double (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2 * q]), "=d"(v[2 * q + 1]) : "r"(a_lo + 16u * q));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[4 + 2 * q]), "=d"(v[4 + 2 * q + 1]) : "r"(a_hi + 16u * q));
+    }
+}
+__device__ __forceinline__ float lds_at(unsigned a, float) { return lds_f32(a); }
+__device__ __forceinline__ double lds_at(unsigned a, double) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32_at(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds_v2_at(unsigned a, float) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2_at(unsigned a, double) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
 }
 // value at the position before the one register j holds (`left` = the previous lane's last position)
 template <typename V> __device__ __forceinline__ V prev8(const V (&v)[8], int j, bool fl, V left) {
@@ -294,6 +336,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
 
     bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * 2 * GRAD_LBINS;     // two sets: one per frame in flight
+    const unsigned bins_a = smem_u32(bins);
     T *acc = (T *)(smem_raw + mp.o_acc) + (size_t)warp * 2 * sp;     // wide mode only: [2][sp] stay / total sums of this warp
     if (FAC) {
         for (int l = lane; l < 2 * GRAD_LBINS; l += 32) bins[l] = 0;
@@ -351,6 +394,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     const int offA = a.ctx.o_fa + lbk * 8 * (int)sizeof(T), offB = a.ctx.o_fb + lbk * 8 * (int)sizeof(T);
     const int offEa = a.ctx.o_ea + lbk * 4, offEb = a.ctx.o_eb + lbk * 4;
     const int offCa = a.ctx.o_ca + lane * (int)sizeof(T), offCb = a.ctx.o_cb + lane * (int)sizeof(T);
+    const int64_t gx_pair_stride = (int64_t)NW * N * L;
+    // fast path: byte offsets inside a record of the two (possibly swapped) halves of this lane's alpha / beta block
+    const unsigned oA_lo = (unsigned)(offA + sw * (int)sizeof(T)), oA_hi = (unsigned)(offA + (4 - sw) * (int)sizeof(T));
+    const unsigned oB_lo = (unsigned)(offB + sw * (int)sizeof(T)), oB_hi = (unsigned)(offB + (4 - sw) * (int)sizeof(T));
+    const bool has0 = lane < lpi, has1 = LP > 32 && lane + 32 < lpi;           // this lane's two FCC labels exist
+    const int offCa0 = a.ctx.o_ca + (has0 ? lane : 0) * (int)sizeof(T), offCb0 = a.ctx.o_cb + (has0 ? lane : 0) * (int)sizeof(T);
+    const int offCa1 = a.ctx.o_ca + (has1 ? lane + 32 : 0) * (int)sizeof(T), offCb1 = a.ctx.o_cb + (has1 ? lane + 32 : 0) * (int)sizeof(T);
     const int offCw = a.ctx.o_cw + ib * RI * (int)sizeof(T), offPw = a.ctx.o_ca + jb * CJ * (int)sizeof(T);
     // (utterance, tile-in-utterance, ring stage, ring pass) are walked: no per-tile divisions
     int wn = q_begin / a.tiles_t, wt = q_begin - wn * a.tiles_t, stage = 0, use = 0;
@@ -420,7 +470,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
             const int ra = 1 + warp, rb = 1 + warp + NW;
             const int rr[2] = {ra, rb};
             const bool act = lane < nblk;
-            const char *rowp[2] = {srec + (size_t)ra * R, srec + (size_t)rb * R};      // this warp's two frame records
+            const unsigned rowa[2] = {smem_u32(srec) + (unsigned)ra * (unsigned)R, smem_u32(srec) + (unsigned)rb * (unsigned)R};   // this warp's two frame records
             T bv[2][8];
             if (FAC) {
                 T av[2][8];
@@ -428,9 +478,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 T fa[2], fb[2];                             // normalising factors of the stored mantissas (x half the product scale)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    lds8sw((const T *)(rowp[u] + offA), sw, av[u]);
-                    lds8sw((const T *)(rowp[u] + offB), sw, bv[u]);
-                    const int wa = *(const int *)(rowp[u] + offEa), wb = *(const int *)(rowp[u] + offEb);
+                    lds8_at(rowa[u] + oA_lo, rowa[u] + oA_hi, av[u]);
+                    lds8_at(rowa[u] + oB_lo, rowa[u] + oB_hi, bv[u]);
+                    const int wa = lds_s32_at(rowa[u] + (unsigned)offEa), wb = lds_s32_at(rowa[u] + (unsigned)offEb);
                     fac_unpack_norm<T>(wa, ea[u], da[u], fa[u]);
                     fac_unpack_norm<T>(wb, eb[u], db[u], fb[u]);
                 }
@@ -438,9 +488,9 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 int ep[2];                                  // exponent of the RAW mantissas of frame t-1 (E + d)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    lds8sw((const T *)(rowp[u] - R + offA), sw, pv[u]);
+                    lds8_at(rowa[u] - (unsigned)R + oA_lo, rowa[u] - (unsigned)R + oA_hi, pv[u]);
                     int e_, d_;
-                    fac_unpack(*(const int *)(rowp[u] - R + offEa), e_, d_);
+                    fac_unpack(lds_s32_at(rowa[u] - (unsigned)R + (unsigned)offEa), e_, d_);
                     ep[u] = e_ + d_;
                 }
                 T ps[2];
@@ -476,7 +526,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         bv[u][j] = bv[u][j] * c2;
-                        FX::add(&bu[lab[j]], FX::to_fix(bv[u][j]));
+                        if constexpr (sizeof(T) == 4) red_shared_s32(bins_a + (unsigned)(lab[j] * 4 + u * GRAD_LBINS * 4), FX::to_fix(bv[u][j]));
+                        else FX::add(&bu[lab[j]], FX::to_fix(bv[u][j]));
                     }
                 }
 #pragma unroll
@@ -502,10 +553,11 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     T al0[2], al1[2], be0[2], be1[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        al0[u] = al1[u] = be0[u] = be1[u] = T(0);
-                        if (lane < lpi) { al0[u] = *(const T *)(rowp[u] + offCa); be0[u] = *(const T *)(rowp[u] + offCb); }
-                        if (LP > 32 && lane + 32 < lpi) { al1[u] = *(const T *)(rowp[u] + offCa + 32 * (int)sizeof(T)); be1[u] = *(const T *)(rowp[u] + offCb + 32 * (int)sizeof(T)); }
-                        g0[u] = al0[u] * be0[u]; g1[u] = al1[u] * be1[u];
+                        // every lane loads (idle lanes re-read element 0 and drop it): no divergent branch around the loads
+                        al0[u] = lds_at(rowa[u] + (unsigned)offCa0, T()); be0[u] = lds_at(rowa[u] + (unsigned)offCb0, T());
+                        al1[u] = be1[u] = T(0);
+                        if (LP > 32) { al1[u] = lds_at(rowa[u] + (unsigned)offCa1, T()); be1[u] = lds_at(rowa[u] + (unsigned)offCb1, T()); }
+                        g0[u] = has0 ? al0[u] * be0[u] : T(0); g1[u] = has1 ? al1[u] * be1[u] : T(0);
                     }
                     T z0 = g0[0] + g1[0], z1 = g0[1] + g1[1];
 #pragma unroll
@@ -519,13 +571,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     g0[u] *= inv[u]; g1[u] *= inv[u];
-                    const T winv = inv[u] * *(const T *)(rowp[u] + a.ctx.o_sc);
+                    const T winv = inv[u] * lds_at(rowa[u] + (unsigned)a.ctx.o_sc, T());
                     T wv[RI];
                     V2 pw[CJ2];
 #pragma unroll
-                    for (int i = 0; i < RI; ++i) wv[i] = ((const T *)(rowp[u] + offCw))[i] * winv;
+                    for (int i = 0; i < RI; ++i) wv[i] = lds_at(rowa[u] + (unsigned)offCw + (unsigned)(i * sizeof(T)), T()) * winv;
 #pragma unroll
-                    for (int j = 0; j < CJ2; ++j) pw[j] = ((const V2 *)(rowp[u] - R + offPw))[j];
+                    for (int j = 0; j < CJ2; ++j) pw[j] = lds_v2_at(rowa[u] - (unsigned)R + (unsigned)offPw + (unsigned)(j * 2 * sizeof(T)), T());
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
                         const V2 w2 = Pk<T>::mk(wv[i], wv[i]);
@@ -534,9 +586,10 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                     }
                 }
             }
+            T *const gx_tile = a.grad_x + ((int64_t)(t0 + warp) * N + n) * L;      // frame t0-1+ra; the second frame is NW frames later
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                T *gx_row = a.grad_x + ((int64_t)(t0 - 1 + rr[u]) * N + n) * L;
+                T *gx_row = gx_tile + (u ? gx_pair_stride : (int64_t)0);
                 T o0 = g0[u], o1 = g1[u];
                 if (FAC) {
                     bin_t *bu = bins + u * GRAD_LBINS;
