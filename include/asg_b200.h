@@ -230,7 +230,9 @@ int asg_logits_backward_fix(int dtype,
  *   1  a finite emission underflowed against its frame's maximum (exp(x - max) == 0),
  *   2  in some frame a block of 8 target positions could hold flushed entries whose alpha*beta product is not negligible (below
  *      2^-24) against the frame's largest product: posterior mass may have been lost,
- *   4  the aligned score of a feasible utterance came out as -inf.
+ *   4  the aligned score of a feasible utterance came out as -inf,
+ *   8  a target label of the utterance lies outside [0, L) (not a range matter, reported through the same word): the reference
+ *      gathers out of bounds there (force_aligned_lattice.cpp:36-60); these kernels clamp the label to [0, L-1] and say so here.
  * Bits 1 and 4 are final after asg_scan / asg_forward, bit 2 after asg_grad / asg_backward / asg_step on the same ctx.  A caller
  * that sees a flag should rerun that batch in ASG_F64 (same API, 8x the range).
  */

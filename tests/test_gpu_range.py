@@ -88,3 +88,38 @@ def test_normalised_inputs_raise_no_flag():
     y = rng.integers(0, L, (N, S))
     f = run(x, A, y, np.full(N, T), np.full(N, S), np.full(N, 1.0 / N), torch.float32)
     assert (f["flags"] == 0).all()
+
+
+def test_out_of_range_labels_are_reported_not_silently_clamped():
+    """The reference gathers out of bounds for a label outside [0, L) (force_aligned_lattice.cpp:36-60).  Here: bit 8 of the
+    utterance's range flags (the label itself is clamped so nothing faults), GraphedASGLoss.check() raises, and
+    ASGLoss(validate_targets=True) raises before the call.  Labels beyond target_lengths are padding and never looked at."""
+    import torch_asg
+    import torch_asg_native as nat
+    dev = "cuda"
+    T, N, L, S = 50, 4, 10, 8
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(T, N, L, generator=g).log_softmax(-1).to(dev)
+    y = torch.randint(0, L, (N, S), generator=g)
+    tl = torch.tensor([8, 5, 8, 3])
+    y[1, 6] = 99          # padding (beyond target_lengths[1] = 5): fine
+    y[3, 7] = -4          # padding
+    y[2, 4] = L           # live and out of range
+    il = torch.full((N,), T)
+    A = torch.zeros(L, L, device=dev)
+    out = nat.fast_asg_gpu_forward(x, y.to(dev), A, il.to(dev), tl.to(dev), T, N, L, S)
+    flags = nat.range_flags(out[5], out[4], False, T, N, L, S).cpu()
+    assert flags.tolist() == [0, 0, 8, 0]
+    crit = torch_asg.ASGLoss(L).to(dev)
+    gc = torch_asg.GraphedASGLoss(crit)
+    xg = x.clone().requires_grad_(True)
+    gc.step(xg, y.to(dev), il.to(dev), tl.to(dev))
+    with pytest.raises(IndexError, match="utterance 2"):
+        gc.check()
+    y[2, 4] = 0
+    gc.step(xg, y.to(dev).clone(), il.to(dev), tl.to(dev))
+    assert gc.check().tolist() == [0, 0, 0, 0]
+    y[2, 4] = -1
+    strict = torch_asg.ASGLoss(L, validate_targets=True).to(dev)
+    with pytest.raises(IndexError, match="utterance 2"):
+        strict(x, y.to(dev), il.to(dev), tl.to(dev))

@@ -17,7 +17,8 @@ enum { SC_R = 0, SC_FULL_BETA = 1, SC_FULL_ALPHA = 2, SC_RB = 3, SC_AL_BETA = 4,
 enum { RF_EMISSION_UNDERFLOW = 1,   // a finite emission lies more than the format's range below its frame's maximum: exp(x - max) = 0
        RF_POSTERIOR_THIN = 2,       // in some frame a block of target positions could hold FLUSHED entries (more than 2^126 below the
                                     // block's maxima) whose alpha*beta product is not negligible against the frame's largest one
-       RF_SCORE_LOST = 4 };         // the aligned score of a feasible utterance came out as -inf
+       RF_SCORE_LOST = 4,           // the aligned score of a feasible utterance came out as -inf
+       RF_LABEL_RANGE = 8 };        // a target label outside [0, L): the reference indexes out of bounds there; here the label was clamped
 
 // typed view of the frame-record array + the context blob (see asg_layout_t)
 template <typename T> struct Ctx {

@@ -775,6 +775,8 @@ __device__ void fac_consumer(const ScanArgs<T> &a, FacSmemView<T> &sm, int W, in
     for (int k = 0; k < Tn; ++k) {
         const int t = BETA ? (Tn - 1 - k) : k;
         if ((k & (FB - 1)) == 0) {
+            __threadfence_block();                                   // this warp's reads of the ring rows of frames < k come first
+            __syncwarp();
             if (lane == 0) st_volatile_s32(&sm.consumed[warp], k);   // frames < k are done with
             const int need = min(k + FB, Tn);
             while (ld_volatile_s32(&sm.flags[0]) < need) __nanosleep(20);
@@ -1014,6 +1016,8 @@ __device__ void fac_consumer_f32(const ScanArgs<float> &a, FacSmemView<float> &s
     const bool edge = BETA ? lane == 31 : lane == 0;
 
     auto ring_sync = [&](int k) {                     // frames < k are done with; frames k .. k+FB-1 must be in the ring
+        __threadfence_block();                        // this warp's reads of the ring rows of frames < k come first
+        __syncwarp();
         if (lane0) st_volatile_s32(&sm.consumed[0], k);
         const int need = min(k + FB, Tn);
         while (ld_volatile_s32(&sm.flags[vec ? 2 : 0]) < need) __nanosleep(20);
@@ -1233,11 +1237,17 @@ __global__ void __launch_bounds__(544) fac_scan_kernel(const ScanArgs<T> a, int 
     if (threadIdx.x < W) sm.consumed[threadIdx.x] = 0;
     for (int l = threadIdx.x; l < RING * up; l += nthreads) sm.uring[l] = T(0);     // incl. the always-zero slots of every row
     const int64_t *yn = a.y + (int64_t)n * a.y_s0;
+    bool bad_label = false;
     for (int s = threadIdx.x; s < sp; s += nthreads) {
         int lab = -1;
-        if (s < Sn) { lab = (int)yn[(int64_t)s * a.y_s1]; lab = max(0, min(L - 1, lab)); }
+        if (s < Sn) {
+            const int64_t raw = yn[(int64_t)s * a.y_s1];
+            bad_label |= raw < 0 || raw >= L;
+            lab = (int)max((int64_t)0, min((int64_t)(L - 1), raw));
+        }
         sm.ylab[s] = lab;
     }
+    if (bad_label) atomicOr(a.ctx.flags(n), RF_LABEL_RANGE);       // rare; reported by asg_range_flags
     __syncthreads();
 
     // ---- per-position transition scores: H_s = A[y_s,y_s], D_s = A[y_{s+1},y_s]; Rb = their max ----

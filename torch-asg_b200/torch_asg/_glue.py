@@ -119,8 +119,13 @@ def bind_native(native):
         _native = native          # the bound native module (torch_asg.sharded calls it directly)
 
         def __init__(self, num_labels, reduction='mean', forward_only=False,
-                     gpu_no_stream_impl=False):
+                     gpu_no_stream_impl=False, validate_targets=False):
             super().__init__()
+            # not in the reference: with validate_targets the labels inside target_lengths are checked against
+            # [0, num_labels) before the call (one device synchronisation) and an IndexError names the utterance; the
+            # reference gathers out of bounds for such labels.  Without it the kernels clamp the label and raise bit 8
+            # of the utterance's range flags (asg_range_flags / GraphedASGLoss.check()).
+            self.validate_targets = validate_targets
             self.num_labels = num_labels
             self.reduction = reduction
             self.forward_only = forward_only
@@ -141,6 +146,13 @@ def bind_native(native):
         def forward(self, inputs, targets, input_lengths=None, target_lengths=None):
             targets, input_lengths, target_lengths = self._lengths(
                 inputs, targets, input_lengths, target_lengths)
+            if self.validate_targets:
+                S = targets.shape[1]
+                live = torch.arange(S, device=targets.device)[None, :] < target_lengths.to(targets.device)[:, None]
+                bad = live & ((targets < 0) | (targets >= self.num_labels))
+                if bool(bad.any()):
+                    n = int(bad.any(dim=1).nonzero()[0])
+                    raise IndexError("ASGLoss: utterance %d has a target label outside [0, %d)" % (n, self.num_labels))
             args = (targets, input_lengths, target_lengths)
             if self.gpu_no_stream_impl or not inputs.is_cuda:
                 per_utt = (FCC.apply(self.transition, inputs, *args)

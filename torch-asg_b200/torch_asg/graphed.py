@@ -338,6 +338,18 @@ class GraphedASGLoss(nn.Module):
         that fp32's ~87 nats of in-frame / in-block dynamic range were exceeded; rerun such a batch in float64."""
         return next(reversed(self._entries.values())).ws.range_flags()
 
+    def check(self):
+        """Synchronise and validate the most recent call: raises IndexError when a target label was outside [0, L) (the kernels
+        clamped it; the reference gathers out of bounds), RuntimeError when a peer exchange timed out, and returns the int32 [N]
+        range flags (all zero unless the emissions were too peaked for this dtype -- rerun that batch in float64)."""
+        flags = self.range_flags
+        f = flags.cpu()
+        if bool((f & 8).any()):
+            raise IndexError("GraphedASGLoss: utterance %d has a target label outside [0, %d)" % (int((f & 8).nonzero()[0]), self.criterion.num_labels))
+        if self._peer is not None and self._peer.status()[1]:
+            raise RuntimeError("GraphedASGLoss: a peer exchange timed out waiting for another rank (epoch %d)" % self._peer.status()[1])
+        return flags
+
     @property
     def global_loss(self):
         """After a backward (or step): the reduced loss over ALL ranks' utterances, from the all-reduced fused buffer."""
