@@ -2,7 +2,7 @@
 """Developer timing script (GPU box): per-phase CUDA-event timings of the native entry points."""
 import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "torch-asg_b200"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.environ.get("ASG_PKG", os.path.join(ROOT, "torch-asg_b200")))
 import torch, numpy as np
 import torch_asg_native as nat
 
