@@ -100,7 +100,16 @@ __device__ __forceinline__ float fast_div(float a, float b) { return a * rcp_(b)
 __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 // posterior bins of the fast path: a shared-memory reduction at a precomputed 32-bit address (no return value, no per-element
 // address arithmetic); float only -- the double bins are 64-bit (add64_shared)
-__device__ __forceinline__ void red_shared_s32(unsigned addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// eight of them under ONE predicate (idle lanes stay out), at base addresses + a compile-time offset
+template <int OFF>
+__device__ __forceinline__ void red8_shared_s32_if(const unsigned (&a)[8], const int (&v)[8], bool pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %16, 0;\n"
+                 "@p red.shared.add.s32 [%0+%17], %8;\n@p red.shared.add.s32 [%1+%17], %9;\n@p red.shared.add.s32 [%2+%17], %10;\n"
+                 "@p red.shared.add.s32 [%3+%17], %11;\n@p red.shared.add.s32 [%4+%17], %12;\n@p red.shared.add.s32 [%5+%17], %13;\n"
+                 "@p red.shared.add.s32 [%6+%17], %14;\n@p red.shared.add.s32 [%7+%17], %15;\n}\n"
+                 ::"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+                   "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"((unsigned)pred), "n"(OFF) : "memory");
+}
 
 // shared-memory map: [per-CTA block][stage 0][stage 1]...   A stage holds TB+1 frame records (the halo record of
 // frame t0-1 first) exactly as they lie in global memory, plus the tile's winv scalars.
@@ -351,9 +360,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     // narrow mode: this lane's block of the current utterance.  accH: posterior mass that STAYED into position j,
     // accQ: all posterior mass at position j (frames >= 1); the moved mass is their difference.
     T hreg[8], dreg[8], accH[8], accQ[8];
-    int lab[8], labm1 = 0;
+    // lab[j]: the shared-memory ADDRESS of the posterior bin of position j's label (set 0 of this warp's bins): the fast path adds
+    // into it without any per-frame address arithmetic; LAB() recovers the label where it is needed (utterance boundaries)
+    unsigned lab[8], labm1 = 0;
+    auto LAB = [&](unsigned v) { return (int)((v - bins_a) / (unsigned)sizeof(bin_t)); };
+    auto LADDR = [&](int l) { return bins_a + (unsigned)l * (unsigned)sizeof(bin_t); };
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { hreg[j] = dreg[j] = accH[j] = accQ[j] = T(0); lab[j] = L; }
+    for (int j = 0; j < 8; ++j) { hreg[j] = dreg[j] = accH[j] = accQ[j] = T(0); lab[j] = LADDR(L); }
 
     // Utterance boundary: the per-position edge sums go, as 64-bit fixed point (order-independent), into the CTA's
     // L x L edge matrix of this utterance; after one barrier they are scaled by the utterance's upstream gradient and
@@ -365,10 +378,11 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
             if (lane < nblk) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (lab[j] < L) {
-                        const int prevlab = prev8(lab, j, fl, labm1);
-                        add64_shared(&gfix[lab[j] * L + lab[j]], FX::edge_fix(accH[j]));
-                        if (lane * 8 + (j ^ sw) >= 1) add64_shared(&gfix[lab[j] * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
+                    const int lj = LAB(lab[j]);
+                    if (lj < L) {
+                        const int prevlab = LAB(prev8(lab, j, fl, labm1));
+                        add64_shared(&gfix[lj * L + lj], FX::edge_fix(accH[j]));
+                        if (lane * 8 + (j ^ sw) >= 1) add64_shared(&gfix[lj * L + prevlab], FX::edge_fix(accQ[j] - accH[j]));
                     }
                     accH[j] = accQ[j] = T(0);
                 }
@@ -400,7 +414,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
     const unsigned oB_lo = (unsigned)(offB + sw * (int)sizeof(T)), oB_hi = (unsigned)(offB + (4 - sw) * (int)sizeof(T));
     const bool has0 = lane < lpi, has1 = LP > 32 && lane + 32 < lpi;           // this lane's two FCC labels exist
     const int offCa0 = a.ctx.o_ca + (has0 ? lane : 0) * (int)sizeof(T), offCb0 = a.ctx.o_cb + (has0 ? lane : 0) * (int)sizeof(T);
-    const int offCa1 = a.ctx.o_ca + (has1 ? lane + 32 : 0) * (int)sizeof(T), offCb1 = a.ctx.o_cb + (has1 ? lane + 32 : 0) * (int)sizeof(T);
+    // (idle lanes of the second label re-read their FIRST element: element 0 would share a bank with element 32)
+    const int offCa1 = a.ctx.o_ca + (has1 ? lane + 32 : (has0 ? lane : 0)) * (int)sizeof(T), offCb1 = a.ctx.o_cb + (has1 ? lane + 32 : (has0 ? lane : 0)) * (int)sizeof(T);
     const int offCw = a.ctx.o_cw + ib * RI * (int)sizeof(T), offPw = a.ctx.o_ca + jb * CJ * (int)sizeof(T);
     // (utterance, tile-in-utterance, ring stage, ring pass) are walked: no per-tile divisions
     int wn = q_begin / a.tiles_t, wt = q_begin - wn * a.tiles_t, stage = 0, use = 0;
@@ -419,12 +434,13 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                 if (FAC) {
                     const int o = buf * sp + min(lane, nblk - 1) * 8;
                     const int4 l0 = *reinterpret_cast<const int4 *>(ylab + o + sw), l1 = *reinterpret_cast<const int4 *>(ylab + o + 4 - sw);
-                    lab[0] = l0.x; lab[1] = l0.y; lab[2] = l0.z; lab[3] = l0.w; lab[4] = l1.x; lab[5] = l1.y; lab[6] = l1.z; lab[7] = l1.w;
+                    lab[0] = LADDR(l0.x); lab[1] = LADDR(l0.y); lab[2] = LADDR(l0.z); lab[3] = LADDR(l0.w);
+                    lab[4] = LADDR(l1.x); lab[5] = LADDR(l1.y); lab[6] = LADDR(l1.z); lab[7] = LADDR(l1.w);
                     lds8sw(hh + o, sw, hreg);
                     lds8sw(din + o, sw, dreg);
                     if (lane >= nblk) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { lab[j] = L; hreg[j] = T(0); dreg[j] = T(0); }
+                        for (int j = 0; j < 8; ++j) { lab[j] = LADDR(L); hreg[j] = T(0); dreg[j] = T(0); }
                     }
                     labm1 = __shfl_up_sync(ASG_FULL_MASK, last8(lab, fl), 1);
                 }
@@ -524,10 +540,18 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
                                      ? Num<T>::ldexp_pos(rcp_(Z[u]), sh[u] + Num<T>::kPostLog2) : T(0);
                     bin_t *bu = bins + u * GRAD_LBINS;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        bv[u][j] = bv[u][j] * c2;
-                        if constexpr (sizeof(T) == 4) red_shared_s32(bins_a + (unsigned)(lab[j] * 4 + u * GRAD_LBINS * 4), FX::to_fix(bv[u][j]));
-                        else FX::add(&bu[lab[j]], FX::to_fix(bv[u][j]));
+                    for (int j = 0; j < 8; ++j) bv[u][j] = bv[u][j] * c2;
+                    // idle lanes stay out: they would all hit ONE trash bin (same-address serialisation; 7.75 wavefronts per
+                    // reduction were measured with them in, the shared-memory pipe's largest single cost)
+                    if constexpr (sizeof(T) == 4) {
+                        int bq[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bq[j] = FX::to_fix(bv[u][j]);
+                        if (u == 0) red8_shared_s32_if<0>(lab, bq, act);
+                        else red8_shared_s32_if<GRAD_LBINS * 4>(lab, bq, act);
+                    } else if (act) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) FX::add(&bu[LAB(lab[j])], FX::to_fix(bv[u][j]));
                     }
                 }
 #pragma unroll
@@ -638,7 +662,7 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         bv[j] = bv[j] * c2;                            // posterior of position 8*lane+j, in fixed-point units
-                        FX::add(&bins[lab[j]], FX::to_fix(bv[j]));
+                        if (act) FX::add(&bins[LAB(lab[j])], FX::to_fix(bv[j]));
                     }
                     if (t >= 1) {
                         T pv[8];
