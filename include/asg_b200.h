@@ -68,7 +68,7 @@ enum {
     ASG_E_DTYPE = -1,   /* dtype is not ASG_F32 / ASG_F64 */
     ASG_E_SHAPE = -2,   /* non-positive T/N/L/S, or S > T (asg.py:119-122 truncates before the boundary) */
     ASG_E_NULL = -3,    /* a required pointer is NULL */
-    ASG_E_UNSUPPORTED = -4, /* shape outside what this build covers: L > 2048, S > 4096 (S > 256 when L > 64), fp64 S > 2048 */
+    ASG_E_UNSUPPORTED = -4, /* shape outside what this build covers: L > 2048, S > 4096 (when L > 64: S > 768 fp32 / S > 384 fp64), fp64 S > 2048 */
     ASG_E_NOGPU = -5    /* no CUDA device / driver: there is no CPU fallback */
 };
 

@@ -513,6 +513,27 @@ def test_large_alphabet_small_case(surf, dtype, tol, path):
         assert rel(v, ref[k], floor) <= tol, (path, k, rel(v, ref[k], floor))
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float64, TOL64)])
+@pytest.mark.parametrize("path", ["fast", "fwdonly"])
+def test_large_alphabet_wide_targets(surf, dtype, tol, path):
+    """L > 64 together with S > 256: several force-aligned consumer warps in gather mode and the every-thread FAC part of the
+    large-alphabet frame kernel (round 1 and most of round 2 refused this shape)."""
+    r = np.random.default_rng(22)
+    T, N, L, S = 330, 3, 80, 300
+    x = r.standard_normal((T, N, L))
+    A = 0.3 * r.standard_normal((L, L))
+    y = r.integers(0, L, (N, S))
+    tl = np.array([S, 261, 40])
+    il = np.array([T, 300, 200])
+    g = r.uniform(0.5, 1.5, N)
+    ref = O.asg_loss(x, y, A, il, tl, g)
+    c = {"x": x, "y": y, "A": A, "il": il, "tl": tl, "g": g}
+    o = run_surface(surf, c, dtype, path)
+    for k, v in o.items():
+        floor = 1.0 if k in ("loss", "full", "aligned") else 1e-30
+        assert rel(v, ref[k], floor) <= tol, (path, k, rel(v, ref[k], floor))
+
+
 def test_cfg4_large_alphabet(surf):
     """T=500 N=128 L=1024 S=100 fp32 (BASELINE configs[3]): the reference cannot run this with a backward pass
     (268 GB path_contrib).  Properties on the whole batch + oracle parity on 2 utterances."""

@@ -86,8 +86,11 @@ static int check_dims(int dtype, int64_t T, int64_t N, int64_t L, int64_t S) {
                     (long long)L, (long long)S);
     if (S > T) return fail(ASG_E_SHAPE, "S (%lld) > T (%lld): truncate targets first (asg.py:119-122)", (long long)S, (long long)T);
     if (L > 2048) return fail(ASG_E_UNSUPPORTED, "this build covers L <= 2048 labels (got %lld)", (long long)L);
-    if (L > ASG_SMALL_L && S > 256)
-        return fail(ASG_E_UNSUPPORTED, "large alphabets (L > 64) are covered for S <= 256 target positions (got %lld)", (long long)S);
+    // large alphabets run the force-aligned scans in gather mode: the emission ring holds S values per frame, 64 frames deep
+    const int64_t s_large = dtype == ASG_F32 ? 768 : 384;
+    if (L > ASG_SMALL_L && S > s_large)
+        return fail(ASG_E_UNSUPPORTED, "large alphabets (L > 64) are covered for S <= %lld target positions in this dtype (got %lld)",
+                    (long long)s_large, (long long)S);
     if (S > 4096) return fail(ASG_E_UNSUPPORTED, "this build covers S <= 4096 target positions (got %lld)", (long long)S);
     if (T > (1 << 24) || N > (1 << 20)) return fail(ASG_E_UNSUPPORTED, "T or N too large");
     return 0;

@@ -577,9 +577,11 @@ constexpr int GL_THREADS = 256;
 constexpr int GL_FRAMES = 8;      // frames per CTA
 
 // One CTA = (utterance, GL_FRAMES consecutive frames).  Per frame: FAC posterior by warp 0 (lane = 8-position block,
-// S <= 256) -> fixed-point label bins in shared memory + edge sums; FCC posterior dense over L by all threads;
+// S <= 256; WIDE: by every thread, S <= 2048) -> fixed-point label bins in shared memory + edge sums; FCC posterior dense over L by all threads;
 // grad_x row written once; u*beta scaled in place by gf * scale_t / Z_t for the GEMM.
-template <typename T, bool FCC, bool FAC>
+// WIDE (S > 256, up to GL_THREADS blocks = 2048 positions): the FAC part runs on ALL threads, one 8-position block per thread; the
+// three warp-level steps (largest product of the frame, its total, the boundary value from the previous block) become CTA-level ones.
+template <typename T, bool FCC, bool FAC, bool WIDE>
 __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const GradArgs<T> a, unsigned long long *edge /*[2][N][sp]*/) {
     extern __shared__ __align__(16) char gl_smem[];
     typedef FixL<T> FX;
@@ -589,7 +591,12 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
     const int64_t tp = a.ctx.tp;
     bin_t *bins = (bin_t *)gl_smem;                         // [L]
     T *red = (T *)(bins + L);                               // [32]
+    int *redi = (int *)(red + 32);                          // [8]     (WIDE)
+    T *xv = (T *)(redi + 8);                                // [GL_THREADS] boundary values of the previous frame (WIDE)
+    int *xe = (int *)(xv + GL_THREADS);                     // [GL_THREADS] and their exponents
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int blk = WIDE ? tid : lane;                      // this thread's 8-position block
+    const bool fac_thread = FAC && (WIDE || warp == 0);
     const int n = blockIdx.y;
     const int t_begin = blockIdx.x * GL_FRAMES;
     const int Tn = (int)a.ctx.il[n];
@@ -600,12 +607,12 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
     T hreg[8], dreg[8], accH[8], accQ[8];
     int lab[8];
     int Sn = 0;
-    if (FAC && warp == 0) {
+    if (fac_thread) {
         Sn = (int)a.ctx.tl[n];
         const int64_t *yn = a.y + (int64_t)n * a.y_s0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int s = lane * 8 + j;
+            const int s = blk * 8 + j;
             lab[j] = -1; hreg[j] = dreg[j] = accH[j] = accQ[j] = T(0);
             if (s < Sn) {
                 lab[j] = max(0, min(L - 1, (int)yn[(int64_t)s * a.y_s1]));
@@ -625,10 +632,10 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
             if (FCC) for (int l = tid; l < lpi; l += GL_THREADS) { a.ctx.fcc_w(row)[l] = T(0); a.ctx.fcc_alpha(row)[l] = T(0); }
             continue;
         }
-        // ---- FAC (warp 0): posterior -> bins, edge sums ----
-        if (FAC && warp == 0) {
-            const bool act = lane < nblk;
-            const int b8 = min(lane, nblk - 1) * 8, be = min(lane, nblk - 1);
+        // ---- FAC (warp 0, or every thread when WIDE): posterior -> bins, edge sums ----
+        if (fac_thread) {
+            const bool act = blk < nblk;
+            const int b8 = min(blk, nblk - 1) * 8, be = min(blk, nblk - 1);
             T av[8], bv[8];
             const T *pa = a.ctx.fac_alpha(row) + b8, *pb = a.ctx.fac_beta(row) + b8;
 #pragma unroll
@@ -643,14 +650,23 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
             for (int j = 0; j < 8; ++j) { bv[j] = (av[j] * fa) * (bv[j] * fb); pm = tmax(pm, bv[j]); ps += bv[j]; }
             const int c = ea + eb;
             const int ce = (act && pm > T(0)) ? c + Num<T>::pexp(pm) : INT_MIN;
-            const int cmax = __reduce_max_sync(ASG_FULL_MASK, ce);
+            int cmax = __reduce_max_sync(ASG_FULL_MASK, ce);
+            if (WIDE) {
+                __syncthreads();
+                if (lane == 0) redi[warp] = cmax;
+                __syncthreads();
+                cmax = redi[0];
+#pragma unroll
+                for (int w = 1; w < GL_THREADS / 32; ++w) cmax = max(cmax, redi[w]);
+            }
             const int sh = Num<T>::block_shift(c, cmax);
-            const T Z = warp_sum((ce != INT_MIN) ? Num<T>::ldexp_pos(ps, sh) : T(0));
+            const T zpart = (ce != INT_MIN) ? Num<T>::ldexp_pos(ps, sh) : T(0);
+            const T Z = WIDE ? block_sum(zpart, red, GL_THREADS / 32) : warp_sum(zpart);
             const T kq = (Z > Num<T>::tiny() && ce != INT_MIN) ? Num<T>::ldexp_pos(T(1) / Z, sh + Num<T>::kPostLog2) : T(0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 bv[j] = bv[j] * kq;
-                if (lab[j] >= 0) FX::add(&bins[lab[j]], FX::to_fix(bv[j]));
+                if (act && lab[j] >= 0) FX::add(&bins[lab[j]], FX::to_fix(bv[j]));
             }
             if (t >= 1) {
                 T pv[8];
@@ -660,9 +676,19 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
                 int ep, dp_;
                 fac_unpack(a.ctx.fac_ea(row - 1)[be], ep, dp_);
                 ep += dp_;
-                T left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
-                const int el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
-                left = (lane == 0) ? T(0) : left * Num<T>::exp2i(min(el - ep, Num<T>::kMaxShift - 8));
+                T left;
+                int el;
+                if (WIDE) {
+                    __syncthreads();                          // (the previous frame's exchange has been read)
+                    xv[tid] = pv[7]; xe[tid] = ep;
+                    __syncthreads();
+                    left = tid ? xv[tid - 1] : T(0);
+                    el = tid ? xe[tid - 1] : ep;
+                } else {
+                    left = __shfl_up_sync(ASG_FULL_MASK, pv[7], 1);
+                    el = __shfl_up_sync(ASG_FULL_MASK, ep, 1);
+                }
+                left = (blk == 0) ? T(0) : left * Num<T>::exp2i_flush(min(el - ep, Num<T>::kMaxShift - 8));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const T stay = hreg[j] * pv[j];
@@ -700,10 +726,10 @@ __global__ void __launch_bounds__(GL_THREADS) grad_large_frame_kernel(const Grad
         __syncthreads();
     }
     // ---- FAC edge sums of this CTA's frames -> global fixed point (integer atomics: order independent) ----
-    if (FAC && warp == 0 && lane < nblk) {
+    if (fac_thread && blk < nblk) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int s = lane * 8 + j;
+            const int s = blk * 8 + j;
             if (lab[j] >= 0) {
                 const T sc = (sizeof(T) == 4) ? T(4) : T(1.0 / 16777216.0);      // kPost units -> 2^32 (2^38) per unit mass
                 atomicAdd(&edge[(int64_t)n * sp + s], (unsigned long long)(long long)llrint((double)(accH[j] * sc)));
@@ -865,12 +891,14 @@ static int launch_grad_large_t(const GradArgs<T> &a, cudaStream_t st) {
     unsigned long long *galfix = (unsigned long long *)((char *)edge + align_up(16 * (size_t)N * a.ctx.sp, 256));
     cudaError_t e = cudaMemsetAsync(edge, 0, align_up(16 * (size_t)N * a.ctx.sp, 256) + (FAC ? sizeof(unsigned long long) * (size_t)L * L : 0), st);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = (size_t)L * 8 + 32 * sizeof(T) + 64;
-    if ((e = cudaFuncSetAttribute(grad_large_frame_kernel<T, FCC, FAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)L * 8 + 32 * sizeof(T) + 8 * sizeof(int) + GL_THREADS * (sizeof(T) + sizeof(int)) + 64;
+    const bool wide = FAC && a.ctx.nblk > 32;
+    auto kern = wide ? grad_large_frame_kernel<T, FCC, FAC, true> : grad_large_frame_kernel<T, FCC, FAC, false>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
     dim3 grid((unsigned)((a.ctx.tp + GL_FRAMES - 1) / GL_FRAMES), N);
     {
         LaunchScope ls(K_GRAD, st);
-        grad_large_frame_kernel<T, FCC, FAC><<<grid, GL_THREADS, smem, st>>>(a, edge);
+        kern<<<grid, GL_THREADS, smem, st>>>(a, edge);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     const int splitk = large_splitk(L);
