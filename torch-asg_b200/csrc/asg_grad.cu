@@ -133,7 +133,7 @@ __host__ __device__ inline GradMap grad_map(size_t eb, size_t rec_bytes, int L, 
     m.o_cscal = take(2 * 2 * eb + 2 * 2 * sizeof(int));      // [2]{gf, ga} then [2]{Tn, Sn}
     m.o_Gal = take(eb * (size_t)L * L);
     m.o_Gf = take(fcc ? eb * (size_t)L * L : 0);
-    m.o_galfix = take(fac ? 8 * 2 * (size_t)L * L : 0);
+    m.o_galfix = take(fac ? 8 * (size_t)L * L : 0);
     m.o_bins = take(fac ? eb * (size_t)nw * 2 * GRAD_LBINS : 0);      // int32 bins for float, int64 for double
     m.o_acc = take((fac && sp > 256) ? eb * (size_t)nw * 2 * sp : 0);
     m.o_bars = take(sizeof(uint64_t) * 3 * 8);
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 #pragma unroll
         for (int j = 0; j < CJ2; ++j) G[i][j] = Pk<T>::mk(T(0), T(0));
 
-    unsigned long long *galfix = (unsigned long long *)(smem_raw + mp.o_galfix);     // [2][L*L] fixed-point edge sums
-    for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) { galfix[e] = 0; galfix[L * L + e] = 0; } }
+    unsigned long long *galfix = (unsigned long long *)(smem_raw + mp.o_galfix);     // [L*L] fixed-point edge sums
+    for (int e = tid; e < L * L; e += ncons) { Gal[e] = T(0); if (FCC) Gf[e] = T(0); if (FAC) galfix[e] = 0; }
 
     bin_t *bins = (bin_t *)(smem_raw + mp.o_bins) + (size_t)warp * 2 * GRAD_LBINS;     // two sets: one per frame in flight
     const unsigned bins_a = smem_u32(bins);
@@ -370,10 +370,10 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
 
     // Utterance boundary: the per-position edge sums go, as 64-bit fixed point (order-independent), into the CTA's
     // L x L edge matrix of this utterance; after one barrier they are scaled by the utterance's upstream gradient and
-    // added to Gal by the thread that owns the element.  Two matrices alternate so one barrier per boundary is enough.
+    // added to Gal by the thread that owns the element.  A second barrier after the owners have zeroed the matrix lets ONE matrix serve every boundary.
     auto flush_fac = [&]() {
         if (!FAC || cur_n < 0) return;
-        unsigned long long *gfix = galfix + (size_t)(nutt & 1) * L * L;
+        unsigned long long *gfix = galfix;
         if (narrow) {
             if (lane < nblk) {
 #pragma unroll
@@ -400,7 +400,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
             Gal[e] += ga * FX::edge_unfix(gfix[e]);
             gfix[e] = 0;
         }
-        ++nutt;
+        cbar();                                 // one matrix (not two alternating ones: its 12.8 kB are worth more as L1), so the
+        ++nutt;                                 // zeroing must be complete before any warp adds the next utterance's sums
     };
 
     // byte offsets of this lane's slices inside a frame record (idle lanes re-read the last block, weight 0)
@@ -923,6 +924,9 @@ static cudaError_t launch_grad_lp(const GradArgs<T> &a_in, cudaStream_t st) {
     a.num_tiles = a.tiles_t * a.d.N;
     cudaError_t e = cudaFuncSetAttribute(grad_kernel<T, LP, FCC, FAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
+    // developer knob: a carve-out of 100 (%) reproduces the L1-starved timing (+3 us at cfg-2: the register spills of 512 threads
+    // are 45 kB of local memory, which 28 kB of L1 cannot hold)
+    if (const char *env = getenv("ASG_GRAD_CARVE")) cudaFuncSetAttribute(grad_kernel<T, LP, FCC, FAC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env));
     int grid = grad_grid_size(device);
     if (grid > a.num_tiles) grid = a.num_tiles;
     {
