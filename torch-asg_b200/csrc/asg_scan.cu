@@ -557,22 +557,30 @@ __device__ void fcc_consumer_f32(const ScanArgs<float> &a, FccSmem<float, LP> &s
         for (int k2 = 1; k2 < CQ2; ++k2)
 #pragma unroll
             for (int r = 0; r < RG; ++r) acc[r] = __ffma2_rn(E[r][k2], p[k2], acc[r]);
-        T zs[RG];
+        // The four column-quarters of a row meet by REDUCE-SCATTER, not all-reduce: lane q only needs rows q and q + 4 of its
+        // group.  Round one (lanes q ^ 2) halves the rows a lane carries, round two (q ^ 1) leaves one per quad: 3 shuffles +
+        // 3 adds per quad of rows instead of 8 + 8.
+        T zs[8];
 #pragma unroll
-        for (int r = 0; r < RG; ++r) zs[r] = acc[r].x + acc[r].y;
-#pragma unroll
-        for (int r = 0; r < RG; ++r) zs[r] += __shfl_xor_sync(ASG_FULL_MASK, zs[r], 1);
+        for (int r = 0; r < 8; ++r) zs[r] = (r < RG) ? acc[r < RG ? r : 0].x + acc[r < RG ? r : 0].y : T(0);
         const T ua0 = BETA ? applied : u0 * applied, ua1 = BETA ? applied : u1 * applied;
+        T zq[2] = {T(0), T(0)};
 #pragma unroll
-        for (int r = 0; r < RG; ++r) zs[r] += __shfl_xor_sync(ASG_FULL_MASK, zs[r], 2);
-        T z0 = zs[0], z1 = T(0);
-#pragma unroll
-        for (int r = 1; r < RG && r < 4; ++r) z0 = (q == r) ? zs[r] : z0;
-        if (RG > 4) {
-            z1 = zs[4];
-#pragma unroll
-            for (int r = 5; r < RG; ++r) z1 = (q == r - 4) ? zs[r] : z1;
+        for (int m = 0; m < 2; ++m) {
+            if (4 * m >= RG) continue;
+            const bool hi2 = (q & 2) != 0, hi1 = (q & 1) != 0;
+            // round one: keep the rows whose owner shares this lane's bit 1
+            T am = hi2 ? zs[4 * m + 2] : zs[4 * m];
+            am += __shfl_xor_sync(ASG_FULL_MASK, hi2 ? zs[4 * m] : zs[4 * m + 2], 2);
+            T bm = T(0);
+            if (4 * m + 1 < RG) {
+                bm = hi2 ? zs[4 * m + 3] : zs[4 * m + 1];
+                bm += __shfl_xor_sync(ASG_FULL_MASK, hi2 ? zs[4 * m + 1] : zs[4 * m + 3], 2);
+            }
+            // round two: keep the row this lane owns
+            zq[m] = (hi1 ? bm : am) + __shfl_xor_sync(ASG_FULL_MASK, hi1 ? am : bm, 1);
         }
+        const T z0 = zq[0], z1 = zq[1];
         T v0 = z0 * ua0, v1 = z1 * ua1;
         if (!has0) v0 = T(0);
         if (!(RG > 4 && has1)) v1 = T(0);
