@@ -288,6 +288,19 @@ int asg_host_submit(asg_host_ctx_t *h,
 int asg_host_wait(asg_host_ctx_t *h);
 
 /*
+ * Target preprocessing on the device (the reference leaves it to the user, README.md:93-94): replabels.
+ * ASG transcripts cannot repeat a label (doc/tech_report.tex:126), so runs are written with "repeat" tokens, wav2letter++
+ * convention (flashlight lib/text packReplabels / unpackReplabels): token first_rep_label + k - 1 (1 <= k <= max_reps) means "the
+ * previous label k MORE times"; a run longer than max_reps + 1 starts over (a a a a, max_reps 2 -> a r2 a).  max_reps = 0 copies.
+ *   pack:   y[N,S] (strides), tl[N] or NULL -> out[N,S] contiguous (never longer than the input), out_len[N]; tail = fill
+ *   unpack: the inverse, into out[N,S_out]; out_len[n] is the FULL unpacked length even when it exceeds S_out (then truncated)
+ */
+int asg_pack_replabels(const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *tl, int64_t N, int64_t S, int64_t first_rep_label,
+                       int64_t max_reps, int64_t fill, int64_t *out, int64_t *out_len, asg_stream_t stream);
+int asg_unpack_replabels(const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *tl, int64_t N, int64_t S, int64_t first_rep_label,
+                         int64_t max_reps, int64_t fill, int64_t *out, int64_t S_out, int64_t *out_len, asg_stream_t stream);
+
+/*
  * The exchange step of a batch-sharded job (one process per GPU, utterances sharded over ranks): the sum over ranks
  * of the fused vector [L*L transition gradient | loss sum | utterance count] that asg_backward / asg_step leave in `fused`.
  * The reference has no multi-GPU path of its own (its users wrap the criterion in DistributedDataParallel, which all-reduces

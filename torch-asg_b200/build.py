@@ -23,7 +23,7 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-ccbin", CXX]
-CU_SOURCES = ["asg_scan.cu", "asg_grad.cu", "asg_large.cu", "asg_viterbi.cu", "asg_peer.cu", "asg_api.cu"]
+CU_SOURCES = ["asg_scan.cu", "asg_grad.cu", "asg_large.cu", "asg_viterbi.cu", "asg_peer.cu", "asg_replabel.cu", "asg_api.cu"]
 HEADERS = [os.path.join(CSRC, "asg_common.cuh"), os.path.join(CSRC, "asg_internal.h"),
            os.path.join(INC, "asg_b200.h")]
 

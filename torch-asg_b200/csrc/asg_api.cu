@@ -416,6 +416,24 @@ int asg_range_flags(int dtype, const void *state, const void *ctx, int64_t T, in
     return cuda_fail((int)cudaGetLastError(), "asg_range_flags");
 }
 
+int asg_pack_replabels(const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *tl, int64_t N, int64_t S, int64_t first_rep_label,
+                       int64_t max_reps, int64_t fill, int64_t *out, int64_t *out_len, asg_stream_t stream) {
+    if (!y || !out || !out_len) return fail(ASG_E_NULL, "asg_pack_replabels: y, out and out_len are required");
+    if (N <= 0 || S <= 0 || max_reps < 0) return fail(ASG_E_SHAPE, "asg_pack_replabels: N, S must be positive and max_reps >= 0");
+    if (S > 8192) return fail(ASG_E_UNSUPPORTED, "asg_pack_replabels covers S <= 8192 (got %lld)", (long long)S);
+    return cuda_fail(replabel_dispatch(true, y, y_s0, y_s1, tl, N, S, first_rep_label, max_reps, fill, out, S, out_len, (cudaStream_t)stream),
+                     "asg_pack_replabels");
+}
+
+int asg_unpack_replabels(const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *tl, int64_t N, int64_t S, int64_t first_rep_label,
+                         int64_t max_reps, int64_t fill, int64_t *out, int64_t S_out, int64_t *out_len, asg_stream_t stream) {
+    if (!y || !out || !out_len) return fail(ASG_E_NULL, "asg_unpack_replabels: y, out and out_len are required");
+    if (N <= 0 || S <= 0 || S_out <= 0 || max_reps < 0) return fail(ASG_E_SHAPE, "asg_unpack_replabels: N, S, S_out must be positive and max_reps >= 0");
+    if (S + S_out > 16384) return fail(ASG_E_UNSUPPORTED, "asg_unpack_replabels covers S + S_out <= 16384 (got %lld)", (long long)(S + S_out));
+    return cuda_fail(replabel_dispatch(false, y, y_s0, y_s1, tl, N, S, first_rep_label, max_reps, fill, out, S_out, out_len, (cudaStream_t)stream),
+                     "asg_unpack_replabels");
+}
+
 size_t asg_viterbi_scratch_bytes(int64_t T, int64_t N, int64_t S) {
     if (T <= 0 || N <= 0 || S <= 0) return 0;
     return align_up(sizeof(unsigned) * (size_t)N * T * viterbi_words(S), 256);

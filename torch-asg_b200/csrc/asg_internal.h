@@ -124,6 +124,8 @@ int grad_grid_size(int device);   // number of persistent CTAs asg_grad launches
 int large_splitk_host(int L);
 size_t large_ws_bytes(size_t elem_bytes, int64_t N, int64_t L);   // asg_large.cu     // K splits of the large-alphabet transition-gradient contraction (asg_large.cu)
 void count_launch(int n = 1);
+int replabel_dispatch(bool pack, const int64_t *y, int64_t y_s0, int64_t y_s1, const int64_t *tl, int64_t N, int64_t S, int64_t first_rep,
+                      int64_t max_reps, int64_t fill, int64_t *out, int64_t S_out, int64_t *out_len, cudaStream_t st);
 int fail(int code, const char *fmt, ...);            // records asg_last_error(), returns code
 int cuda_fail(int e, const char *where);             // 0 stays 0
 void release_side_slots();          // asg_scan.cu: asg_release()

@@ -393,6 +393,26 @@ std::tuple<Tensor, Tensor> viterbi_align(Tensor &inputs, Tensor &targets, Tensor
     return {scores, path};
 }
 
+// not in the reference: replabel packing / unpacking of integer targets on the device (asg_pack_replabels / asg_unpack_replabels)
+std::tuple<Tensor, Tensor> replabels(Tensor &targets, Tensor &target_lengths, int64_t first_rep_label, int64_t max_reps, int64_t fill,
+                                     bool pack, int64_t S_out) {
+    check_cuda(targets, "targets");
+    TORCH_CHECK(targets.dim() == 2 && targets.scalar_type() == at::kLong, "targets must be an int64 [N,S] tensor");
+    const int64_t N = targets.size(0), S = targets.size(1);
+    c10::cuda::CUDAGuard guard(targets.device());
+    Tensor tl = as_device_long(target_lengths, targets, "target_lengths", N);
+    if (pack) S_out = S;
+    Tensor out = at::empty({N, S_out}, targets.options());
+    Tensor len = at::empty({N}, targets.options());
+    if (pack)
+        check_rc(asg_pack_replabels(targets.data_ptr<int64_t>(), targets.stride(0), targets.stride(1), tl.data_ptr<int64_t>(), N, S, first_rep_label,
+                                    max_reps, fill, out.data_ptr<int64_t>(), len.data_ptr<int64_t>(), current_stream()));
+    else
+        check_rc(asg_unpack_replabels(targets.data_ptr<int64_t>(), targets.stride(0), targets.stride(1), tl.data_ptr<int64_t>(), N, S, first_rep_label,
+                                      max_reps, fill, out.data_ptr<int64_t>(), S_out, len.data_ptr<int64_t>(), current_stream()));
+    return {out, len};
+}
+
 // ---- extras (not in the reference): introspection for tests and bench.py ------------------------
 Tensor ctx_scalars(Tensor &ctx, bool is_double, int64_t T, int64_t N, int64_t L, int64_t S) {
     const asg_layout_t lay = layout_of(is_double ? ASG_F64 : ASG_F32, T, N, L, S);
@@ -440,6 +460,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def("allreduce", &PeerComm::allreduce)
         .def("status", &PeerComm::status);
     m.def("range_flags", &range_flags, "per-utterance range report of (state, ctx) (asg_range_flags), int32 [N] (not in the reference)");
+    m.def("replabels", &replabels, "replabel packing (pack=True) / unpacking of int64 targets: (out[N,S_out], lengths[N]) (not in the reference)");
     m.def("viterbi_align", &viterbi_align, "Viterbi forced alignment: (scores[N], path[N,T]) (not in the reference)");
     m.def("logits_backward_fix", &logits_backward_fix,
           "fused log_softmax + ASG: in-place correction of grad_x for infeasible utterances (not in the reference)");
