@@ -276,10 +276,11 @@ int asg_host_loss(asg_host_ctx_t *h,
                   void *loss, void *grad_x, void *grad_A);
 
 /*
- * The same, split for pipelining: asg_host_submit() enqueues the copies and kernels on the context's private
- * stream and returns; asg_host_wait() blocks until that context's results are in host memory.  Several contexts
- * may be in flight at once (one submit per context between waits): the H2D of one step then overlaps the
- * kernels of the previous one and the D2H of the one before.  Host buffers must be pinned for the overlap.
+ * The same, split for pipelining: asg_host_submit() enqueues the copies on the context's private stream and the kernels
+ * on the device's one compute stream (events hand over in both directions) and returns; asg_host_wait() blocks until that
+ * context's results are in host memory.  Several contexts may be in flight at once (one submit per context between waits):
+ * the kernels of all contexts then run back to back in submission order while the H2D of later steps and the D2H of earlier
+ * ones overlap them.  Host buffers must be pinned for the overlap.  Thread-safe across contexts.
  */
 int asg_host_submit(asg_host_ctx_t *h,
                     const void *x, const void *A, const int64_t *y, const int64_t *il, const int64_t *tl,
@@ -328,7 +329,8 @@ int asg_peer_status(asg_peer_t *p, uint64_t *epoch, uint64_t *timed_out_epoch);
 int asg_peer_destroy(asg_peer_t *p);
 
 /* Destroys the side streams and events the library created for asg_scan()'s FCC/FAC overlap (one set per
- * (device, caller stream) pair).  Optional; call when no work of this library is in flight. */
+ * (device, caller stream) pair) and the per-device compute stream of the asg_host_* path.  Optional; call when no work of
+ * this library is in flight. */
 void asg_release(void);
 
 const char *asg_last_error(void);
