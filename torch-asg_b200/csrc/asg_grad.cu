@@ -404,20 +404,8 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
         ++nutt;                                 // zeroing must be complete before any warp adds the next utterance's sums
     };
 
-    // byte offsets of this lane's slices inside a frame record (idle lanes re-read the last block, weight 0)
-    const int lbk = min(lane, max(nblk, 1) - 1);
-    const int offA = a.ctx.o_fa + lbk * 8 * (int)sizeof(T), offB = a.ctx.o_fb + lbk * 8 * (int)sizeof(T);
-    const int offEa = a.ctx.o_ea + lbk * 4, offEb = a.ctx.o_eb + lbk * 4;
-    const int offCa = a.ctx.o_ca + lane * (int)sizeof(T), offCb = a.ctx.o_cb + lane * (int)sizeof(T);
     const int64_t gx_pair_stride = (int64_t)NW * N * L;
-    // fast path: byte offsets inside a record of the two (possibly swapped) halves of this lane's alpha / beta block
-    const unsigned oA_lo = (unsigned)(offA + sw * (int)sizeof(T)), oA_hi = (unsigned)(offA + (4 - sw) * (int)sizeof(T));
-    const unsigned oB_lo = (unsigned)(offB + sw * (int)sizeof(T)), oB_hi = (unsigned)(offB + (4 - sw) * (int)sizeof(T));
     const bool has0 = lane < lpi, has1 = LP > 32 && lane + 32 < lpi;           // this lane's two FCC labels exist
-    const int offCa0 = a.ctx.o_ca + (has0 ? lane : 0) * (int)sizeof(T), offCb0 = a.ctx.o_cb + (has0 ? lane : 0) * (int)sizeof(T);
-    // (idle lanes of the second label re-read their FIRST element: element 0 would share a bank with element 32)
-    const int offCa1 = a.ctx.o_ca + (has1 ? lane + 32 : (has0 ? lane : 0)) * (int)sizeof(T), offCb1 = a.ctx.o_cb + (has1 ? lane + 32 : (has0 ? lane : 0)) * (int)sizeof(T);
-    const int offCw = a.ctx.o_cw + ib * RI * (int)sizeof(T), offPw = a.ctx.o_ca + jb * CJ * (int)sizeof(T);
     // (utterance, tile-in-utterance, ring stage, ring pass) are walked: no per-tile divisions
     int wn = q_begin / a.tiles_t, wt = q_begin - wn * a.tiles_t, stage = 0, use = 0;
     for (int q = q_begin; q < q_end; ++q) {
@@ -488,6 +476,20 @@ __global__ void __launch_bounds__((GRAD_MAX_CWARPS + 4) * 32, 1) grad_kernel(con
             const int rr[2] = {ra, rb};
             const bool act = lane < nblk;
             const unsigned rowa[2] = {smem_u32(srec) + (unsigned)ra * (unsigned)R, smem_u32(srec) + (unsigned)rb * (unsigned)R};   // this warp's two frame records
+            // The per-lane offsets into a record are RECOMPUTED here for every tile (a dozen integer instructions from `lane`
+            // and the layout constants in the parameter bank) instead of living in ~14 registers across the whole kernel: kept
+            // alive they were the registers ptxas spilled, and the spill reloads sat at the head of every tile.  The empty asm
+            // makes the lane index opaque so that the compiler does not hoist them back out of the loop.
+            int lv = lane;
+            asm volatile("" : "+r"(lv));
+            const int lbk_ = min(lv, max(nblk, 1) - 1);
+            const unsigned oA_lo = (unsigned)(a.ctx.o_fa + lbk_ * 8 * (int)sizeof(T) + sw * (int)sizeof(T)), oA_hi = oA_lo + (unsigned)((4 - 2 * sw) * (int)sizeof(T));
+            const unsigned oB_lo = (unsigned)(a.ctx.o_fb + lbk_ * 8 * (int)sizeof(T) + sw * (int)sizeof(T)), oB_hi = oB_lo + (unsigned)((4 - 2 * sw) * (int)sizeof(T));
+            const int offEa = a.ctx.o_ea + lbk_ * 4, offEb = a.ctx.o_eb + lbk_ * 4;
+            const int l0_ = has0 ? lv : 0, l1_ = has1 ? lv + 32 : l0_;
+            const int offCa0 = a.ctx.o_ca + l0_ * (int)sizeof(T), offCb0 = a.ctx.o_cb + l0_ * (int)sizeof(T);
+            const int offCa1 = a.ctx.o_ca + l1_ * (int)sizeof(T), offCb1 = a.ctx.o_cb + l1_ * (int)sizeof(T);
+            const int offCw = a.ctx.o_cw + (lv >> 2) * RI * (int)sizeof(T), offPw = a.ctx.o_ca + (lv & 3) * CJ * (int)sizeof(T);
             T bv[2][8];
             if (FAC) {
                 T av[2][8];
